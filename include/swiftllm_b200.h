@@ -1,0 +1,136 @@
+/*
+ * swiftllm_b200.h - C ABI of the B200-native (sm_100a) data plane that replaces every kernel in
+ * swiftLLM's `swiftllm/worker/kernels/` plus the native `swiftllm_c` module.
+ *
+ * Drop-in boundary: the reference binds its kernels as Python functions on torch tensors (one wrapper
+ * per op, in place / into caller-provided outputs, current CUDA stream).  This library exports exactly
+ * one entry point per wrapper, taking raw device pointers, sizes, a dtype tag and the stream; the host
+ * package `swiftllm_b200/worker/kernels/*.py` binds them with ctypes under the reference's own names and
+ * signatures (see INTEGRATION.md for the stub a swiftLLM maintainer would add).
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the parameter name says `host_`;
+ *   - tensors are contiguous in the reference's layouts (cited per function);
+ *   - all functions enqueue on `stream` (a cudaStream_t) and return immediately;
+ *   - return value: 0 on success, non-zero on error (`sllm_last_error()` gives the message).  Invalid
+ *     shapes are rejected before anything is launched (the reference raises AssertionError there);
+ *   - no CPU fallback exists: on a non-sm_100 device every launch fails with an error.
+ *
+ * Reference paths below are relative to the swiftLLM repository root.
+ */
+#ifndef SWIFTLLM_B200_H
+#define SWIFTLLM_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SLLM_ABI_VERSION 1
+
+typedef enum { SLLM_F16 = 0, SLLM_BF16 = 1 } sllm_dtype_t;
+typedef void* sllm_stream_t; /* cudaStream_t */
+
+/* ---- library ---- */
+int sllm_abi_version(void);
+const char* sllm_last_error(void);          /* thread-local message of the last failing call */
+int sllm_device_check(int device);          /* 0 iff `device` is compute capability 10.x */
+
+/* ---- RMSNorm: swiftllm/worker/kernels/rmsnorm.py:26-37 (rmsnorm_inplace), :67-89 (fused_add_rmsnorm_inplace)
+ * x [num_tokens, hidden] in place; weight [hidden].  fused: residual <- x + residual (rounded to dtype),
+ * x <- rmsnorm(residual) * weight.  hidden % 8 == 0. */
+int sllm_rmsnorm_inplace(void* x, const void* weight, float eps, int64_t num_tokens, int hidden,
+                         sllm_dtype_t dtype, sllm_stream_t stream);
+int sllm_fused_add_rmsnorm_inplace(void* x, void* residual, const void* weight, float eps, int64_t num_tokens,
+                                   int hidden, sllm_dtype_t dtype, sllm_stream_t stream);
+
+/* ---- Rotary embedding: swiftllm/worker/kernels/rotary_emb.py:44-58 (rotary_embedding_inplace)
+ * q [T, nq, D], k [T, nkv, D] in place; cos/sin [T, D/2] (infer_state.position_cos/sin).  NeoX half-split.
+ * D % 16 == 0. */
+int sllm_rotary_embedding_inplace(void* q, void* k, const void* cos, const void* sin, int64_t num_tokens,
+                                  int num_q_heads, int num_kv_heads, int head_dim, sllm_dtype_t dtype,
+                                  sllm_stream_t stream);
+
+/* ---- SwiGLU gate: swiftllm/worker/kernels/silu_and_mul.py:25-34 (silu_and_mul_inplace)
+ * x [T, 2*ffn_inter_dim] = [up | gate]; x[:, :F] <- up * silu(gate).  F % 8 == 0. */
+int sllm_silu_and_mul_inplace(void* x, int64_t num_tokens, int64_t ffn_inter_dim, sllm_dtype_t dtype,
+                              sllm_stream_t stream);
+
+/* ---- KV-cache store: swiftllm/worker/kernels/kvcache_mgmt.py:81-122 (store_kvcache)
+ * k,v [num_tokens, nkv, D] (prefill tokens first, then one row per decoding seq);
+ * caches [num_blocks, num_layers, nkv, block_size, D]; block_table int32 [*, max_blocks_per_seq];
+ * seq_ids int32 [num_prefill_seqs + num_decoding_seqs]. */
+int sllm_store_kvcache(const void* k, const void* v, void* k_cache, void* v_cache, const int32_t* block_table,
+                       const int32_t* seq_ids, const int32_t* prefill_seq_start_locs,
+                       const int32_t* prefill_seq_lens, const int32_t* decoding_seq_lens, int num_prefill_seqs,
+                       int num_decoding_seqs, int64_t num_prefill_tokens, int max_prefill_len, int cur_layer,
+                       int num_layers, int num_kv_heads, int block_size, int head_dim, int max_blocks_per_seq,
+                       sllm_dtype_t dtype, sllm_stream_t stream);
+
+/* ---- Paged (decode) attention: swiftllm/worker/kernels/paged_attn.py:152-222 (paged_attention)
+ * q [Bd, nq, D]; o [Bd, nq*D]; seq_ids = infer_state.seq_ids[num_prefill_seqs:]; seq_lens = decoding_seq_lens.
+ * seq_block_size: tokens per flash-decoding split (multiple of block_size); 0 = let the library choose
+ * (v1 single pass when the batch alone fills the GPU, v2 split + merge otherwise).
+ * workspace: fp32 scratch for split partials, >= sllm_paged_attention_workspace_bytes(...) bytes
+ * (the reference allocates mid_o / mid_o_logexpsum per call, paged_attn.py:170-180). */
+int64_t sllm_paged_attention_workspace_bytes(int num_decoding_seqs, int num_q_heads, int head_dim, int max_seq_len,
+                                             int seq_block_size, int num_kv_heads);
+int sllm_paged_attention(const void* q, const void* k_cache, const void* v_cache, const int32_t* block_table,
+                         const int32_t* seq_ids, const int32_t* seq_lens, void* o, void* workspace,
+                         int64_t workspace_bytes, float softmax_scale, int num_decoding_seqs, int max_seq_len,
+                         int seq_block_size, int cur_layer, int num_layers, int num_q_heads, int num_kv_heads,
+                         int block_size, int head_dim, int max_blocks_per_seq, int64_t num_blocks,
+                         sllm_dtype_t dtype, sllm_stream_t stream);
+
+/* ---- Prefill attention: swiftllm/worker/kernels/prefill_attn.py:102-139 (prefill_attention) and the
+ * flash_attn_varlen_func call it stands for (swiftllm/worker/layers/transformer_layer.py:86-96).
+ * Causal, varlen, packed: q,o [Tp, nq, D]; k,v [Tp, nkv, D]; start_locs/seq_lens int32 [num_prefill_seqs]. */
+int sllm_prefill_attention(const void* q, const void* k, const void* v, void* o, const int32_t* prefill_seq_start_locs,
+                           const int32_t* prefill_seq_lens, float softmax_scale, int num_prefill_seqs,
+                           int max_prefill_len, int64_t num_prefill_tokens, int num_q_heads, int num_kv_heads,
+                           int head_dim, sllm_dtype_t dtype, sllm_stream_t stream);
+
+/* ---- Block-table maintenance: swiftllm/worker/kernels/block_mgmt.py:26-46, :66-80, :106-127
+ * block_table int32 [max_seqs, max_blocks_per_seq]; num_seq_allocated_blocks int32 [max_seqs];
+ * is_block_free uint8/bool [num_blocks]; candidate_blocks int64 [sum(block_needed)];
+ * block_needed int32 [batch]; block_needed_cumsum int32 [batch] (inclusive). */
+int sllm_set_block_table_and_num_seq_alloc_blocks(int32_t* num_seq_allocated_blocks, int32_t* block_table,
+                                                  const int64_t* candidate_blocks, const int32_t* seq_ids,
+                                                  const int32_t* block_needed, const int32_t* block_needed_cumsum,
+                                                  int batch_size, int max_blocks_per_seq, sllm_stream_t stream);
+int sllm_unset_block_table_and_num_seq_alloc_blocks(int32_t* num_seq_allocated_blocks, const int32_t* block_table,
+                                                    const int32_t* seq_ids, uint8_t* is_block_free, int batch_size,
+                                                    int max_blocks_per_seq, sllm_stream_t stream);
+/* allocated_cumsum int32 [batch] (inclusive cumsum of num_seq_allocated_blocks[seq_ids]);
+ * gathered_block_ids int32 [allocated_cumsum[batch-1]] */
+int sllm_gather_allocated_blocks_and_unset(int32_t* num_seq_allocated_blocks, const int32_t* block_table,
+                                           const int32_t* seq_ids, uint8_t* is_block_free,
+                                           const int32_t* allocated_cumsum, int32_t* gathered_block_ids,
+                                           int batch_size, int max_blocks_per_seq, sllm_stream_t stream);
+
+/* ---- Sync-free block allocation (replaces swiftllm/worker/block_manager.py:43-79: assert + .item() +
+ * torch.nonzero).  One launch: for seq i (batch order) needs max(0, cdiv(target_lens[i], block_size) -
+ * num_seq_allocated_blocks[seq_ids[i]]) blocks, taken lowest-free-id first - the reference's order - and
+ * appended to the block table.  Writes the new ids (int64, batch order) to new_blocks_out (capacity
+ * new_blocks_capacity; may be NULL) and {num_new_blocks, error_flag} to status_out (int32[2], error_flag:
+ * 1 = not enough free blocks, 2 = a sequence already holds more blocks than its target; on error nothing
+ * is modified). */
+int sllm_allocate_blocks_for_seqs(int32_t* num_seq_allocated_blocks, int32_t* block_table, uint8_t* is_block_free,
+                                  const int32_t* seq_ids, const int32_t* target_lens, int batch_size,
+                                  int block_size, int64_t num_blocks, int max_blocks_per_seq,
+                                  int64_t* new_blocks_out, int64_t new_blocks_capacity, int32_t* status_out,
+                                  sllm_stream_t stream);
+
+/* ---- Block swapping: csrc/src/block_swapping.cpp:22-85 (swiftllm_c.swap_blocks, csrc/src/entrypoints.cpp:5-7)
+ * host_src_ids/host_dst_ids: HOST arrays of n block ids.  k_swap/v_swap: HOST memory (pinned or pageable),
+ * k_cache/v_cache: device.  block_bytes = bytes of one block (all layers/heads) of k_cache.
+ * Consecutive (src,dst) runs are coalesced into one copy each, as the reference does. */
+int sllm_swap_blocks(const int64_t* host_src_ids, const int64_t* host_dst_ids, int64_t n, int is_swap_in,
+                     void* k_cache, void* v_cache, void* host_k_swap, void* host_v_swap, int64_t block_bytes,
+                     sllm_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SWIFTLLM_B200_H */

@@ -1,0 +1,45 @@
+"""Engine configuration.  The first nine fields and their CLI flags are the reference's
+(swiftllm/engine_config.py:4-84); the trailing fields (with defaults) are additions for the B200 data plane."""
+import argparse
+import dataclasses
+
+
+@dataclasses.dataclass
+class EngineConfig:
+    # Model loading parameters
+    model_path: str
+    use_dummy: bool
+
+    # PagedAttention-related parameters
+    block_size: int
+    gpu_mem_utilization: float
+    num_cpu_blocks: int
+    max_seqs_in_block_table: int
+    max_blocks_per_seq: int
+
+    # Scheduling-related parameters
+    max_batch_size: int
+    max_tokens_in_batch: int
+
+    # ---- additions ----
+    dtype: str = "float16"          # "float16" (the reference's hard-coded dtype) or "bfloat16"
+    tp_size: int = 1                # tensor-parallel world size (heads / FFN columns), one process per GPU
+    tp_rank: int = 0
+    pin_swap_space: bool = True     # the reference's swap space is pageable (model.py:158-159)
+    use_cuda_graph: bool = False    # capture pure-decode steps into CUDA graphs
+
+    @staticmethod
+    def add_cli_args(parser: argparse.ArgumentParser):
+        parser.add_argument("--model-path", type=str, required=True,
+                            help="Path to the model directory (config.json + safetensors / pytorch_model.bin)")
+        parser.add_argument("--use-dummy", action="store_true", help="Use dummy weights (mainly for profiling)")
+        parser.add_argument("--block-size", type=int, default=16, help="Block size for PagedAttention")
+        parser.add_argument("--gpu-mem-utilization", type=float, default=0.97, help="Fraction of GPU memory to be used")
+        parser.add_argument("--num-cpu-blocks", type=int, default=2048, help="Number of CPU blocks")
+        parser.add_argument("--max-seqs-in-block-table", type=int, default=4096,
+                            help="Maximum number of sequences in the block table")
+        parser.add_argument("--max-blocks-per-seq", type=int, default=32768, help="Maximum number of blocks per sequence")
+        parser.add_argument("--max-batch-size", type=int, default=512, help="Maximum batch size")
+        parser.add_argument("--max-tokens-in-batch", type=int, default=32768, help="Maximum number of tokens in a batch")
+        parser.add_argument("--dtype", type=str, default="float16", choices=["float16", "bfloat16"])
+        parser.add_argument("--use-cuda-graph", action="store_true")

@@ -1,0 +1,104 @@
+"""GPU-resident block table / free map, API of the reference's BlockManager (swiftllm/worker/block_manager.py:5-103).
+
+Same observable state (`block_table`, `num_seq_allocated_blocks`, `is_block_free`, `num_free_blocks`) and the same
+allocation order (lowest free id first, batch order) - block ids are bit-exact with the reference.  What changed:
+allocation is ONE kernel launch with no host<->device sync (the reference does assert(...).all(), .item() and
+torch.nonzero, block_manager.py:50,70,75).  The host keeps a mirror of `num_seq_allocated_blocks` so that
+exhaustion is detected on the host (RuntimeError, as in the reference) without reading the device.
+"""
+import numpy as np
+import torch
+
+from .kernels.block_mgmt import (allocate_blocks_for_seqs as _allocate_kernel,
+                                 gather_allocated_blocks_and_unset,
+                                 unset_block_table_and_num_seq_alloc_blocks)
+
+
+class BlockManager:
+    def __init__(self, device_name: str, num_blocks: int, max_seqs_in_block_table: int, max_blocks_per_seq: int,
+                 block_size: int, device="cuda"):
+        self.device_name = device_name
+        self.num_free_blocks = num_blocks
+        self.num_blocks = num_blocks
+        self.block_size = block_size
+        self.max_blocks_per_seq = max_blocks_per_seq
+
+        # seq_id |-> number of blocks allocated for this sequence
+        self.num_seq_allocated_blocks = torch.zeros((max_seqs_in_block_table,), dtype=torch.int32, device=device)
+        # (seq_id, block_index) |-> block_id   (rows are only defined up to num_seq_allocated_blocks[seq_id])
+        self.block_table = torch.empty((max_seqs_in_block_table, max_blocks_per_seq), dtype=torch.int32, device=device)
+        # block_id |-> whether this block is free or not
+        self.is_block_free = torch.ones((num_blocks,), dtype=torch.bool, device=device)
+
+        self._host_nsab = np.zeros((max_seqs_in_block_table,), dtype=np.int64)   # host mirror
+        self._status = torch.zeros((2,), dtype=torch.int32, device=device)
+
+    @staticmethod
+    def _to_list(t, given):
+        if given is not None:
+            return [int(x) for x in given]
+        return t.tolist()            # device sync: only when the caller has no host copy
+
+    def allocate_blocks_for_seqs(self, seq_ids: torch.Tensor, target_lens: torch.Tensor, *,
+                                 seq_ids_list=None, target_lens_list=None, want_new_blocks: bool = True) -> torch.Tensor:
+        """Make sure seq #i has ceil(target_lens[i] / block_size) blocks.  Returns the new block ids (int64,
+        batch order), like the reference (useful for swapping).  Pass the host lists to avoid a device sync."""
+        sids = self._to_list(seq_ids, seq_ids_list)
+        lens = self._to_list(target_lens, target_lens_list)
+        idx = np.asarray(sids, dtype=np.int64)
+        target = (np.asarray(lens, dtype=np.int64) + (self.block_size - 1)) // self.block_size
+        have = self._host_nsab[idx] if len(sids) else np.zeros((0,), dtype=np.int64)
+        assert (have <= target).all(), \
+            f"(On {self.device_name}) Logic error: Some sequences have more blocks already allocated than needed."
+        if len(sids) and int(target.max()) > self.max_blocks_per_seq:
+            raise RuntimeError(f"sequence needs {int(target.max())} blocks > max_blocks_per_seq={self.max_blocks_per_seq}")
+        total = int((target - have).sum())
+        if total > self.num_free_blocks:
+            raise RuntimeError(f"No enough free blocks available on {self.device_name} ({self.num_blocks} in total, "
+                               f"{self.num_free_blocks} free, {total} requested)")
+        new_blocks = torch.empty((total,), dtype=torch.int64, device=self.block_table.device) if want_new_blocks else None
+        if len(sids) and total > 0:
+            if seq_ids.dtype != torch.int32:
+                seq_ids = seq_ids.to(torch.int32)
+            if target_lens.dtype != torch.int32:
+                target_lens = target_lens.to(torch.int32)
+            _allocate_kernel(self.num_seq_allocated_blocks, self.block_table, self.is_block_free,
+                             seq_ids.contiguous(), target_lens.contiguous(), self.block_size,
+                             new_blocks if (want_new_blocks and total > 0) else None, self._status)
+            self._host_nsab[idx] = target
+            self.num_free_blocks -= total
+        return new_blocks
+
+    def check_device_status(self):
+        """Debug/test helper (syncs): the allocator kernel's own error flag."""
+        n, err = self._status.tolist()
+        if err:
+            raise RuntimeError(f"device-side block allocation failed on {self.device_name} (flag {err})")
+        return n
+
+    def free_blocks_for_seqs(self, seq_ids: torch.Tensor, *, seq_ids_list=None):
+        sids = self._to_list(seq_ids, seq_ids_list)
+        if not sids:
+            return
+        idx = np.asarray(sids, dtype=np.int64)
+        self.num_free_blocks += int(self._host_nsab[idx].sum())
+        self._host_nsab[idx] = 0
+        unset_block_table_and_num_seq_alloc_blocks(self.num_seq_allocated_blocks, self.block_table,
+                                                   seq_ids.to(torch.int32), self.is_block_free)
+
+    def gather_allocated_blocks_and_free(self, seq_ids: torch.Tensor, *, seq_ids_list=None) -> torch.Tensor:
+        sids = self._to_list(seq_ids, seq_ids_list)
+        idx = np.asarray(sids, dtype=np.int64)
+        total = int(self._host_nsab[idx].sum()) if sids else 0
+        gathered = gather_allocated_blocks_and_unset(self.num_seq_allocated_blocks, self.block_table,
+                                                     seq_ids.to(torch.int32), self.is_block_free, total_blocks=total)
+        if sids:
+            self._host_nsab[idx] = 0
+        self.num_free_blocks += total
+        return gathered
+
+    def get_num_allocated_blocks(self, seq_ids: torch.Tensor) -> torch.Tensor:
+        return self.num_seq_allocated_blocks[seq_ids.long()]
+
+    def get_num_allocated_blocks_host(self, seq_ids_list) -> list:
+        return self._host_nsab[np.asarray(seq_ids_list, dtype=np.int64)].tolist()

@@ -1,0 +1,36 @@
+"""Reference: swiftllm/worker/kernels/kvcache_mgmt.py (store_kvcache :81-122)."""
+import torch
+
+from swiftllm_b200 import _lib
+from swiftllm_b200.worker.infer_state import LlamaInferState
+
+
+def store_kvcache(
+    k: torch.Tensor,
+    v: torch.Tensor,
+    k_cache: torch.Tensor,
+    v_cache: torch.Tensor,
+    block_table: torch.Tensor,
+    model_config,
+    engine_config,
+    infer_state: LlamaInferState,
+    cur_layer: int
+):
+    assert k.is_contiguous()
+    assert v.is_contiguous()
+    assert k_cache.is_contiguous()
+    assert v_cache.is_contiguous()
+    assert block_table.is_contiguous()
+    assert infer_state.seq_ids.is_contiguous()
+    assert infer_state.decoding_seq_lens.is_contiguous()
+    assert block_table.dtype == torch.int32 and infer_state.seq_ids.dtype == torch.int32
+    _lib.require_device(k_cache)
+    num_layers, nkv, bs, D = k_cache.shape[1:]
+    _lib.check(_lib.lib().sllm_store_kvcache(
+        k.data_ptr(), v.data_ptr(), k_cache.data_ptr(), v_cache.data_ptr(), block_table.data_ptr(),
+        infer_state.seq_ids.data_ptr(),
+        _lib.ptr(infer_state.prefill_seq_start_locs), _lib.ptr(infer_state.prefill_seq_lens),
+        _lib.ptr(infer_state.decoding_seq_lens),
+        infer_state.num_prefill_seqs, infer_state.num_decoding_seqs, infer_state.num_prefill_tokens,
+        infer_state.max_prefill_len, cur_layer, num_layers, nkv, bs, D, block_table.shape[1],
+        _lib.dtype_tag(k.dtype), _lib.stream()), "store_kvcache")

@@ -1,0 +1,54 @@
+"""CPU: the C-ABI library loads and exports every symbol include/swiftllm_b200.h declares (no compute calls)."""
+import ctypes
+import os
+import re
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared():
+    src = open(os.path.join(ROOT, "include", "swiftllm_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(sllm_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_header_declares_expected_surface():
+    names = _declared()
+    for n in ["sllm_rmsnorm_inplace", "sllm_fused_add_rmsnorm_inplace", "sllm_rotary_embedding_inplace",
+              "sllm_silu_and_mul_inplace", "sllm_store_kvcache", "sllm_paged_attention", "sllm_prefill_attention",
+              "sllm_set_block_table_and_num_seq_alloc_blocks", "sllm_unset_block_table_and_num_seq_alloc_blocks",
+              "sllm_gather_allocated_blocks_and_unset", "sllm_allocate_blocks_for_seqs", "sllm_swap_blocks"]:
+        assert n in names
+
+
+def test_library_exports_every_declared_symbol():
+    from swiftllm_b200 import _lib
+    assert os.path.exists(_lib.LIB_PATH), "build with `python -m swiftllm_b200.build`"
+    l = ctypes.CDLL(_lib.LIB_PATH)
+    for n in _declared():
+        assert hasattr(l, n), f"{n} declared in the header but not exported"
+    assert set(_declared()) == set(_lib.SIGNATURES), "ctypes signature table out of sync with the header"
+    assert _lib.lib().sllm_abi_version() == 1
+
+
+def test_invalid_arguments_are_rejected_before_launch():
+    """Shape validation runs on the host and needs no GPU (the reference raises AssertionError here)."""
+    from swiftllm_b200 import _lib
+    l = _lib.lib()
+    assert l.sllm_rmsnorm_inplace(None, None, 1e-5, 4, 12, 0, None) != 0         # hidden % 8 != 0
+    assert b"multiple of 8" in l.sllm_last_error()
+    assert l.sllm_paged_attention(1, 1, 1, 1, 1, 1, 1, None, 0, 1.0, 1, 16, 0, 0, 1, 4, 2, 16, 96, 4, 4, 0, None) != 0
+    assert b"head_dim" in l.sllm_last_error()
+    assert l.sllm_silu_and_mul_inplace(None, 0, 256, 7, None) == 0              # empty batch is a no-op
+    assert l.sllm_swap_blocks(None, None, 0, 1, None, None, None, None, 16, None) == 0
+
+
+def test_no_silent_fallback_without_cuda():
+    import pytest
+    import torch
+    from swiftllm_b200.worker.kernels.rmsnorm import rmsnorm_inplace
+    if torch.cuda.is_available():
+        pytest.skip("CPU-only check")
+    x = torch.zeros(2, 64, dtype=torch.float16)
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        rmsnorm_inplace(x, torch.ones(64, dtype=torch.float16), 1e-5)
