@@ -1,0 +1,371 @@
+#!/usr/bin/env python
+"""bench.py - decode tokens/s of the paged-attention data plane (BASELINE.json metric).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]            # this implementation
+  python bench.py --impl reference ...                            # CPU arm: torch-eager oracle port on host cores
+  torchrun --nproc-per-node N bench.py --gpus N ...               # N > 1: tensor parallel (heads / FFN columns)
+
+Workload (BASELINE.json configs[1]): Llama-3-8B shapes, bf16, pure decode, batch 256, every sequence at
+seq_len 4096, block_size 16, synthetic seeded weights N(0, 0.02) and a KV cache pre-filled with N(0, 1).
+A "step" is one LlamaModel.forward over the batch = one new token per sequence.
+
+One JSON line on stdout (rank 0).  Keys beyond the base contract:
+  value      device-resident throughput: K CUDA-graph replays of the decode step, token ids fed back on the device
+  e2e        the same step through the public API (LlamaModel.forward with host lists): per step one pinned H2D copy
+             of the metadata and one D2H read of the sampled tokens inside the timed region
+  roofline   paged-decode kernel: algorithmic bytes / mean CUDA-event duration of its launches over K eager steps
+  cpu_baseline  the oracle (CPU torch-eager restatement of the reference forward) on a bounded sample
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+METRIC = "decode_tokens_per_s"
+UNIT = "tokens/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", type=str, default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=256)
+    ap.add_argument("--seqlen", type=int, default=4096)
+    ap.add_argument("--model", type=str, default="llama3-8b", choices=["llama3-8b", "llama3-70b", "tiny"])
+    ap.add_argument("--layers", type=int, default=0, help="override the layer count (debug only; marks the run reduced)")
+    ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-prefill", action="store_true")
+    ap.add_argument("--cpu-sample-seqs", type=int, default=8)
+    ap.add_argument("--profile-range", type=int, default=0,
+                    help="profiling aid: run this many eager decode steps inside cudaProfilerStart/Stop and exit "
+                         "(use with ncu --profile-from-start off); prints no bench line")
+    return ap.parse_args()
+
+
+def model_dict(name, layers=0):
+    from swiftllm_b200.model_config import LLAMA3_8B, LLAMA3_70B
+    if name == "llama3-8b":
+        d = dict(LLAMA3_8B)
+    elif name == "llama3-70b":
+        d = dict(LLAMA3_70B)
+    else:
+        d = dict(model_type="llama", num_hidden_layers=2, num_attention_heads=8, num_key_value_heads=2, hidden_size=1024,
+                 vocab_size=1024, max_position_embeddings=8192, intermediate_size=2048, rope_theta=500000.0,
+                 rms_norm_eps=1e-5, hidden_act="silu", rope_scaling=None)
+    if layers > 0:
+        d["num_hidden_layers"] = layers
+    return d
+
+
+# --------------------------------------------------------------------------- clocks
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.p = None
+        self.idx = gpu_index
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                       "-i", str(self.idx)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.p.terminate()
+        try:
+            out, _ = self.p.communicate(timeout=5)
+        except Exception:
+            self.p.kill(); out = ""
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in out.strip().splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------- CPU arm (oracle port)
+def cpu_decode_sample(cfg_full: dict, batch: int, seqlen: int, sample_seqs: int, steps: int = 1, warmup: int = 0):
+    """Torch-eager CPU forward (oracle/model.py) on a bounded sample of the workload: `sample_seqs` of the `batch`
+    sequences at the full sequence length, 1 and 2 of the L layers, fp32 on all host cores.  The per-layer and
+    pre/post-layer times are extrapolated linearly to L layers and to the full batch (decode attention and GEMV-like
+    GEMMs scale linearly in sequences on a CPU).  Returns tokens/s of the whole job + a description."""
+    from oracle.model import OracleLlama, OracleWeights
+    torch.set_num_threads(os.cpu_count() or 1)
+    L = cfg_full["num_hidden_layers"]
+    bs = 16
+    nblk = sample_seqs * ((seqlen + bs - 1) // bs)
+    NL = 2
+    cfg = dict(cfg_full); cfg["num_hidden_layers"] = NL
+    w = OracleWeights.random(cfg, dtype=torch.float32, seed=0, std=0.02)
+    m = OracleLlama(cfg, w, block_size=bs, num_blocks=nblk, num_cpu_blocks=0, max_seqs_in_block_table=sample_seqs,
+                    max_blocks_per_seq=(seqlen + bs - 1) // bs, attn="fast", dtype=torch.float32)
+    g = torch.Generator().manual_seed(1)
+    m.k_cache.normal_(generator=g); m.v_cache.normal_(generator=g)
+    ids = [[int(t)] for t in torch.randint(0, cfg["vocab_size"], (sample_seqs,), generator=g)]
+    sids = list(range(sample_seqs))
+    lens = [seqlen] * sample_seqs
+    for _ in range(max(1, warmup)):
+        m.forward(ids, sids, lens)
+    tl, tp = [], []
+    for _ in range(max(1, steps)):
+        m.forward(ids, sids, lens)
+        tl.append(m.last_times["layers"] / NL); tp.append(m.last_times["pre_post"])
+    t_layer, t_prepost = statistics.median(tl), statistics.median(tp)
+    del m, w
+    t_full_sample = L * t_layer + t_prepost
+    scale = batch / sample_seqs
+    tok_s = batch / (t_full_sample * scale)
+    sample = (f"{sample_seqs} of {batch} sequences at seq_len {seqlen}, fp32, {NL} of {L} layers timed "
+              f"(t_layer={t_layer:.3f}s, t_pre+post={t_prepost:.3f}s), extrapolated linearly to {L} layers and {batch} sequences")
+    return tok_s, sample, t_full_sample * scale
+
+
+def run_reference(args):
+    """`--impl reference`: the reference's CPU-executable restatement (oracle port; the reference itself is Python +
+    Triton and cannot run without a GPU/interpreter at this size) timed on the host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cfg = model_dict(args.model, args.layers)
+    t0 = time.perf_counter()
+    tok_s, sample, t_step = cpu_decode_sample(cfg, args.batch, args.seqlen, args.cpu_sample_seqs,
+                                              steps=max(1, min(args.steps, 3)), warmup=min(args.warmup, 1))
+    cores = os.cpu_count() or 1
+    line = {"impl": "reference", "metric": METRIC, "value": tok_s, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": t_step * 1e3, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f32 (CPU oracle port of the bf16 path)", "data": "synthetic",
+            "config": workload_config(args, cfg, 1),
+            "cpu_baseline": {"value": tok_s, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": tok_s, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0, "wall_s": time.perf_counter() - t0}
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, cfg, n):
+    return {"workload": f"{args.model} pure decode, batch {args.batch}, seq_len {args.seqlen}, block_size 16 "
+                        f"(BASELINE.json configs[1])",
+            "layers": cfg["num_hidden_layers"], "global_batch": args.batch, "seq_len": args.seqlen,
+            "parallelism": f"tp{n}", "l2": "inputs larger than L2 (KV working set and weights >> 126 MB)"}
+
+
+# --------------------------------------------------------------------------- GPU arm
+def run_ours(args):
+    import torch.distributed as dist
+    import swiftllm_b200
+    from swiftllm_b200 import _lib
+    from swiftllm_b200.worker.kernels import paged_attn as pa_mod
+    from swiftllm_b200.worker.weight import synthetic_getter
+
+    n = args.gpus
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    assert world == n, f"--gpus {n} but WORLD_SIZE={world}: launch with torchrun --nproc-per-node {n}"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if n > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    cfg = model_dict(args.model, args.layers)
+    mc = swiftllm_b200.LlamaModelConfig(cfg)
+    B, S, bs = args.batch, args.seqlen, 16
+    blocks_per_seq = (S + bs - 1) // bs
+    ec = swiftllm_b200.EngineConfig(model_path="", use_dummy=False, block_size=bs, gpu_mem_utilization=0.97, num_cpu_blocks=0,
+                                    max_seqs_in_block_table=B, max_blocks_per_seq=blocks_per_seq + 8, max_batch_size=B,
+                                    max_tokens_in_batch=max(B, 8192), dtype="bfloat16", tp_size=n, tp_rank=rank,
+                                    use_cuda_graph=not args.no_graph)
+    model = swiftllm_b200.LlamaModel(ec, mc)
+    model.load_weights(synthetic_getter(seed=0, std=0.02, device=dev))
+    num_blocks = B * blocks_per_seq + 64
+    model.init_kvcache_and_swap(num_blocks)
+    g = torch.Generator(device=dev); g.manual_seed(1234 + rank)
+    chunk = max(1, num_blocks // 64)
+    for s in range(0, num_blocks, chunk):                      # N(0,1) KV so softmax sees realistic, finite data
+        model.k_cache[s:s + chunk].normal_(generator=g)
+        model.v_cache[s:s + chunk].normal_(generator=g)
+    torch.cuda.synchronize()
+
+    gen = torch.Generator().manual_seed(7)
+    ids0 = [[int(t)] for t in torch.randint(0, mc.vocab_size, (B,), generator=gen)]
+    sids = list(range(B))
+    lens = [S] * B
+
+    def barrier():
+        if n > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if n > 1:
+            t = torch.tensor([ms], device=dev); dist.all_reduce(t, op=dist.ReduceOp.MAX); ms = float(t.item())
+        return ms
+
+    # ---- e2e: public API, host lists in, host ints out
+    state = {"ids": ids0}
+
+    def step_e2e():
+        toks = model.forward(state["ids"], sids, lens)            # H2D metadata + D2H tokens inside
+        state["ids"] = [[t] for t in toks]
+
+    for _ in range(max(args.warmup, 3)):
+        step_e2e()
+    if args.profile_range > 0:
+        model.engine_config.use_cuda_graph = False
+        model.forward(state["ids"], sids, lens)
+        torch.cuda.synchronize()
+        torch.cuda.profiler.start()
+        for _ in range(args.profile_range):
+            model.forward(state["ids"], sids, lens)
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
+        return
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
+    launches0 = _lib.LAUNCH_CALLS
+    ms_e2e = timed(step_e2e, args.steps)
+    e2e_calls = _lib.LAUNCH_CALLS - launches0
+
+    # ---- value: device-resident (CUDA-graph replay with on-device token feedback), or eager forward_async
+    graph = None
+    if not args.no_graph and model._graphs:
+        graph = next(iter(model._graphs.values()))
+
+    def step_resident():
+        if graph is not None:
+            graph["meta"][:B].copy_(graph["tokens"].to(torch.int32))     # next step's ids = sampled tokens, on device
+            graph["graph"].replay()
+        else:
+            model.forward_async(state["ids"], sids, lens)
+
+    for _ in range(max(args.warmup, 3)):
+        step_resident()
+    ms_val = timed(step_resident, args.steps)
+    clk = clocks.stop() if rank == 0 else None
+
+    # ---- roofline of the dominant kernel (paged decode attention): eager steps with events around each launch
+    model.engine_config.use_cuda_graph = False
+    pa_mod.TIMING_EVENTS = []
+    l0 = _lib.LAUNCH_CALLS
+    model.forward(state["ids"], sids, lens)
+    launches_per_step = _lib.LAUNCH_CALLS - l0
+    pa_mod.TIMING_EVENTS = []
+    for _ in range(args.steps):
+        model.forward_async(state["ids"], sids, lens)
+    torch.cuda.synchronize()
+    durs = [a.elapsed_time(b) for a, b in pa_mod.TIMING_EVENTS]
+    pa_mod.TIMING_EVENTS = None
+    model.engine_config.use_cuda_graph = not args.no_graph
+    nkv_l, nq_l = mc.num_kv_heads // n, mc.num_q_heads // n
+    alg_bytes = sum(lens) * nkv_l * mc.head_dim * 2 * 2 + 2 * B * nq_l * mc.head_dim * 2
+    pa_ms = statistics.mean(durs)
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (measured copy bandwidth)"
+    else:
+        peak, peak_src = 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
+    achieved = alg_bytes / (pa_ms * 1e-3) / 1e9
+
+    # ---- optional: prefill tokens/s (secondary metric of BASELINE.json)
+    prefill = None
+    if not args.no_prefill:
+        try:
+            model.free_seqs_resources(sids)
+            Bp, Lp = 4, 4096
+            pids = [torch.randint(0, mc.vocab_size, (Lp,), generator=gen).tolist() for _ in range(Bp)]
+            psids = list(range(Bp))
+
+            def step_prefill():
+                model.forward(pids, psids, [])
+                model.free_seqs_resources(psids)
+            for _ in range(2):
+                step_prefill()
+            ms_p = timed(step_prefill, 3)
+            prefill = {"value": Bp * Lp / (ms_p / 3 * 1e-3), "unit": UNIT, "batch": Bp, "prompt_len": Lp}
+        except Exception as e:  # noqa: BLE001
+            prefill = {"error": str(e)[:200]}
+
+    if rank != 0:
+        if n > 1:
+            dist.barrier(); dist.destroy_process_group()
+        return
+
+    cpu = None
+    if n == 1 and not args.no_cpu_baseline:
+        tok_s, sample, _ = cpu_decode_sample(cfg, B, S, args.cpu_sample_seqs)
+        cpu = {"value": tok_s, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port", "sample": sample}
+
+    ms_step = ms_val / args.steps
+    line = {
+        "metric": METRIC, "value": B / (ms_step * 1e-3), "unit": UNIT, "n_gpus": n, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "bf16",
+        "data": "synthetic", "config": workload_config(args, cfg, n),
+        "e2e": {"value": B / (ms_e2e / args.steps * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
+                "h2d_bytes_per_step": 3 * B * 4, "d2h_bytes_per_step": B * 8},
+        "gpu_launches": launches_per_step * args.steps,
+        "gpu_launches_note": f"{launches_per_step} native (libswiftllm_b200.so) launch calls per decode step "
+                             f"({'replayed from a CUDA graph' if graph is not None else 'eager'}); GEMMs/embedding/argmax are library calls on top",
+        "roofline": {"kernel": "paged_attn_kernel (decode attention)", "bound": "hbm", "achieved": achieved, "peak": peak,
+                     "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                     "algorithmic_bytes_per_launch": alg_bytes, "mean_launch_ms": pa_ms, "launches_timed": len(durs),
+                     "how": "CUDA events around every paged_attention launch over K eager decode steps on the launching stream"},
+        "clocks": clk,
+        "cpu_baseline": cpu,
+        "prefill": prefill,
+    }
+    if args.layers:
+        line["reduced"] = "layer count overridden: NOT a valid BASELINE measurement"
+    print(json.dumps(line), flush=True)
+    if n > 1:
+        dist.barrier(); dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -167,6 +167,29 @@ def paged_attention_exact(q, k_cache, v_cache, block_table, seq_ids, seq_lens, s
     return out if out_dtype is None else out.to(out_dtype)
 
 
+def paged_attention_fast(q, k_cache, v_cache, block_table, seq_ids, seq_lens, softmax_scale, block_size, cur_layer,
+                         out_dtype=None):
+    """Same definition as paged_attention_exact (paged_attn.py:224-259) as vectorised torch-eager fp32: pages gathered
+    with index_select, GQA group handled by a batched matmul (no K/V replication).  This is the CPU baseline arm of
+    bench.py (`cpu_baseline`, `--impl reference`)."""
+    Bd, nq, D = q.shape
+    nkv = k_cache.shape[2]
+    g = nq // nkv
+    out = torch.empty((Bd, nq, D), dtype=torch.float32)
+    kl, vl = k_cache[:, cur_layer], v_cache[:, cur_layer]                  # [num_blocks, nkv, bs, D] views
+    for i in range(Bd):
+        L = int(seq_lens[i])
+        nb = (L + block_size - 1) // block_size
+        ids = torch.as_tensor(np.asarray(block_table[int(seq_ids[i])][:nb]), dtype=torch.long)
+        K = kl.index_select(0, ids).permute(1, 0, 2, 3).reshape(nkv, nb * block_size, D)[:, :L].float()
+        V = vl.index_select(0, ids).permute(1, 0, 2, 3).reshape(nkv, nb * block_size, D)[:, :L].float()
+        s = torch.matmul(q[i].view(nkv, g, D).float(), K.transpose(1, 2)) * softmax_scale      # [nkv, g, L]
+        p = torch.softmax(s, dim=-1)
+        out[i] = torch.matmul(p, V).reshape(nq, D)
+    out = out.reshape(Bd, nq * D)
+    return out if out_dtype is None else out.to(out_dtype)
+
+
 def paged_attention_phase1(q, k_cache, v_cache, block_table, seq_ids, seq_lens, softmax_scale,
                            block_size, cur_layer, seq_block_size, num_seq_blocks):
     """paged_attn.py:9-108 in the reference's rounding order (as executed by the

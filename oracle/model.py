@@ -59,7 +59,8 @@ class OracleWeights:
 class OracleLlama:
     """The worker API of model.py on CPU.  `attn` selects how attention is evaluated:
        "ref"   - reference rounding order (paged_attention_ref_order; fp32-softmax prefill stand-in),
-       "exact" - fp64 definitions."""
+       "exact" - fp64 definitions,
+       "fast"  - the same definitions as vectorised fp32 torch-eager (CPU baseline arm of bench.py)."""
 
     def __init__(self, cfg: dict, weights: OracleWeights, *, block_size=16, num_blocks=64, num_cpu_blocks=8,
                  max_seqs_in_block_table=64, max_blocks_per_seq=64, attn="ref", dtype=torch.float16):
@@ -103,8 +104,11 @@ class OracleLlama:
         bt = self.gpu_block_manager.block_table
         scale = self.D ** -0.5
 
+        import time as _time
+        t_start = _time.perf_counter()
         x = self.w.wte[torch.tensor(flat, dtype=torch.long)]            # pre_layer.py:19
         res = torch.zeros_like(x)                                       # model.py:237
+        t_layers0 = _time.perf_counter()
         for li, lw in enumerate(self.w.layers):                         # transformer_layer.py:31-130
             x, res = K.fused_add_rmsnorm(x, res, lw.attn_norm, self.eps)
             q = F.linear(x, lw.q_proj).view(T, self.nq, self.D)
@@ -127,6 +131,9 @@ class OracleLlama:
                 if self.attn == "exact":
                     od = K.paged_attention_exact(q[Tp:], self.k_cache, self.v_cache, bt, sids, decoding_seq_lens_list,
                                                  scale, self.block_size, li, self.dtype)
+                elif self.attn == "fast":
+                    od = K.paged_attention_fast(q[Tp:], self.k_cache, self.v_cache, bt, sids, decoding_seq_lens_list,
+                                                scale, self.block_size, li, self.dtype)
                 else:
                     od = K.paged_attention_ref_order(q[Tp:], self.k_cache, self.v_cache, bt, sids, decoding_seq_lens_list,
                                                      scale, self.block_size, li, S, nsb)
@@ -136,12 +143,17 @@ class OracleLlama:
             ug = F.linear(o, lw.up_gate_proj)
             ug = K.silu_and_mul(ug)
             x = F.linear(ug[:, : self.F], lw.down_proj)
+        t_layers1 = _time.perf_counter()
         x = x + res                                                     # model.py:247
         last_idx = [s + n - 1 for s, n in zip(starts, prefill_lens)] + list(range(Tp, T))   # post_layer.py:24-31
         last = K.rmsnorm(x[torch.tensor(last_idx, dtype=torch.long)], self.w.final_norm, self.eps)
         logits = F.linear(last, self.w.lm_head)
         self.last_logits = logits
-        return torch.argmax(logits, dim=1).tolist()
+        toks = torch.argmax(logits, dim=1).tolist()
+        t_end = _time.perf_counter()
+        # wall-clock split of the last call (used by bench.py's CPU baseline extrapolation)
+        self.last_times = {"layers": t_layers1 - t_layers0, "pre_post": (t_end - t_start) - (t_layers1 - t_layers0)}
+        return toks
 
     # model.py:361-399
     def _swap(self, seq_ids_list, is_swap_in):

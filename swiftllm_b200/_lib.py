@@ -63,7 +63,13 @@ def lib() -> ctypes.CDLL:
     return _lib
 
 
+# number of native calls that enqueue device work since import (bench.py reports it as `gpu_launches`)
+LAUNCH_CALLS = 0
+
+
 def check(rc: int, what: str = ""):
+    global LAUNCH_CALLS
+    LAUNCH_CALLS += 1
     if rc != 0:
         msg = lib().sllm_last_error().decode("utf-8", "replace")
         raise RuntimeError(f"swiftllm_b200 native call failed{(' in ' + what) if what else ''}: {msg} (code {rc})")

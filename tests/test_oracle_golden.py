@@ -157,3 +157,12 @@ def test_model_end_to_end_matches_reference(golden):
                 assert np.array_equal(bm.block_table[s, : n[s]], ref[s, : n[s]])
     assert torch.equal(bits(m.k_cache), bits(T(z["k_cache_final"])))
     assert torch.equal(bits(m.v_cache), bits(T(z["v_cache_final"])))
+
+
+def test_fast_paged_attention_equals_definition(golden):
+    """The vectorised fp32 CPU-baseline attention is the same function as the fp64 definition."""
+    for c in ("c1", "c2"):
+        args, S, nsb, o_ref = _paged(golden("paged_attention"), c)
+        a = K.paged_attention_fast(*args)
+        b = K.paged_attention_exact(*args)
+        assert (a.double() - b).abs().max() <= 1e-5 * b.abs().max()
