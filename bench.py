@@ -211,9 +211,10 @@ def run_ours(args):
     model.init_kvcache_and_swap(num_blocks)
     g = torch.Generator(device=dev); g.manual_seed(1234 + rank)
     chunk = max(1, num_blocks // 64)
-    for s in range(0, num_blocks, chunk):                      # N(0,1) KV so softmax sees realistic, finite data
-        model.k_cache[s:s + chunk].normal_(generator=g)
-        model.v_cache[s:s + chunk].normal_(generator=g)
+    with torch.inference_mode():
+        for s in range(0, num_blocks, chunk):                  # N(0,1) KV so softmax sees realistic, finite data
+            model.k_cache[s:s + chunk].normal_(generator=g)
+            model.v_cache[s:s + chunk].normal_(generator=g)
     torch.cuda.synchronize()
 
     gen = torch.Generator().manual_seed(7)

@@ -335,7 +335,8 @@ class LlamaModel:
         with torch.cuda.graph(graph):
             tokens = step(self.gpu_block_manager, self.k_cache, self.v_cache)
         torch.cuda.synchronize()
-        return dict(graph=graph, meta=meta, host=host, tokens=tokens)
+        # `last` / `empty` are read by the captured kernels on every replay: keep them alive with the graph
+        return dict(graph=graph, meta=meta, host=host, tokens=tokens, keep=(last, empty))
 
     # ------------------------------------------------------------------ swap / free
     def _swap(self, seq_ids_list: list, is_swap_in: bool):

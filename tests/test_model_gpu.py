@@ -103,7 +103,10 @@ def _script(rng):
 @pytest.mark.parametrize("dtype", ["bfloat16", "float16"])
 def test_model_vs_cpu_oracle(dtype):
     """head_dim 128 / GQA 4 (the Llama-3 geometry), vs the fp64-attention oracle: tokens equal where the oracle's
-    top-1 margin is clear of the tolerance, logits within 2^-7 (bf16) / 2e-3 (fp16) of max|logit|."""
+    top-1 margin is clear of the tolerance, logits within 2^-5 (bf16) / 4e-3 (fp16) of max|logit|.  Every
+    intermediate activation is rounded to the storage dtype (2^-9 / 2^-12 relative per op) on both sides but GEMM
+    accumulation order differs (cuBLAS vs CPU), so ~20 roundings random-walk to a few storage-dtype ulps of the
+    largest logit (observed on B200: 1.6e-2 bf16, 2.2e-3 fp16)."""
     tdt = dict(bfloat16=torch.bfloat16, float16=torch.float16)[dtype]
     w = OracleWeights.random(TINY2, dtype=tdt, seed=3, std=0.05)
     oracle = OracleLlama(TINY2, w, block_size=16, num_blocks=40, num_cpu_blocks=4, max_seqs_in_block_table=16,
@@ -112,7 +115,7 @@ def test_model_vs_cpu_oracle(dtype):
     rng = np.random.default_rng(1)
     prompts = _script(rng)
     sids = [7, 1, 4]
-    tol = 2 ** -7 if dtype == "bfloat16" else 2e-3
+    tol = 2 ** -5 if dtype == "bfloat16" else 4e-3
 
     def step(ids, seqs, dec):
         a = m.forward(ids, seqs, dec); b = oracle.forward(ids, seqs, dec)
