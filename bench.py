@@ -365,7 +365,8 @@ def main():
     if args.impl == "reference":
         run_reference(args)
     else:
-        run_ours(args)
+        with torch.inference_mode():
+            run_ours(args)
 
 
 if __name__ == "__main__":

@@ -4,6 +4,7 @@
 #include <vector>
 
 #include "common.cuh"
+#include "tc_helpers.cuh"
 
 namespace sllm {
 
@@ -24,6 +25,24 @@ int check_launch(const char* what) {
     }
     return 0;
 }
+
+namespace tc {
+// cuTensorMapEncodeTiled through the runtime (no link-time dependency on libcuda)
+TensorMapEncodeFn get_tensor_map_encoder() {
+    static TensorMapEncodeFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = (TensorMapEncodeFn)p;
+        cudaGetLastError();
+    }
+    return fn;
+}
+}  // namespace tc
 
 }  // namespace sllm
 

@@ -11,6 +11,8 @@
 //     merge kernel, same (normalised o, log2-sum-exp) partial format as the reference) otherwise.
 // HBM roofline: algorithmic bytes per launch = sum_i len_i * nkv * D * 2 (K and V) * sizeof(T)
 //               + 2 * Bd * nq * D * sizeof(T)  (SURVEY.md §8d).
+#include <stdlib.h>
+
 #include "mma_helpers.cuh"
 
 namespace sllm {
@@ -255,18 +257,32 @@ static int num_sms() {
     return g_num_sms;
 }
 
-// Returns tokens per split (multiple of 64).  Fixed by the caller when seq_block_size > 0.
+// Tokens per flash-decoding split (a multiple of 128), shared by both kernel generations so the workspace size
+// does not depend on which one runs.  Fixed by the caller when seq_block_size > 0.
 static int choose_split_tokens(int num_seqs, int nkv, int max_seq_len, int seq_block_size) {
     if (seq_block_size > 0) return seq_block_size;
-    const int64_t slots = 2LL * num_sms();                     // 2 resident CTAs per SM
     const int64_t pairs = (int64_t)num_seqs * nkv;
-    int64_t want = (4 * slots + pairs - 1) / pairs;            // aim for >= 4 waves worth of CTAs
-    if (want <= 1) return PA_MAX_SPLIT_TOKENS;                 // v1: one CTA per (sequence, kv head), any length
+    const int64_t want = (6LL * num_sms() + pairs - 1) / pairs;    // aim for >= 6 work items per SM
+    if (want <= 1) return PA_MAX_SPLIT_TOKENS;                     // v1: one item per (sequence, kv head)
     int64_t st = (max_seq_len + want - 1) / want;
-    st = ((st + PA_TILE - 1) / PA_TILE) * PA_TILE;
+    st = ((st + 127) / 128) * 128;
     if (st < 256) st = 256;
     if (st > PA_MAX_SPLIT_TOKENS) st = PA_MAX_SPLIT_TOKENS;
     return (int)st;
+}
+
+// generation 2 (paged_attn_tc.cu)
+bool tc_paged_supported(int head_dim, int block_size, int nq, int nkv, int64_t num_blocks, int num_layers);
+int launch_paged_tc(const void* q, const void* k_cache, const void* v_cache, const int32_t* block_table, const int32_t* seq_ids,
+                    const int32_t* seq_lens, void* o, float* part_o, float* part_lse, float scale_log2e, int num_seqs,
+                    int split_tokens, int num_splits, int cur_layer, int num_layers, int nq, int nkv, int max_blocks_per_seq,
+                    int64_t num_blocks, sllm_dtype_t dtype, int num_sms, cudaStream_t stream);
+
+// SLLM_PAGED_ATTN_GEN=1 forces the cp.async/mma.sync kernel (A/B measurements, debugging); default: tcgen05/TMA
+// whenever the shape is covered (head_dim 128, block_size 16).
+static int forced_generation() {
+    const char* e = getenv("SLLM_PAGED_ATTN_GEN");      // re-read every call so tests can toggle it
+    return (e && e[0] == '1') ? 1 : (e && e[0] == '2') ? 2 : 0;
 }
 
 template <typename T, int D>
@@ -312,7 +328,6 @@ int sllm_paged_attention(const void* q, const void* k_cache, const void* v_cache
                          int seq_block_size, int cur_layer, int num_layers, int nq, int nkv, int block_size,
                          int head_dim, int max_blocks_per_seq, int64_t num_blocks, sllm_dtype_t dtype,
                          sllm_stream_t stream) {
-    (void)num_blocks;
     SLLM_REQUIRE(num_decoding_seqs >= 0, "paged_attention: negative batch");
     if (num_decoding_seqs == 0) return 0;
     SLLM_REQUIRE(q && k_cache && v_cache && block_table && seq_ids && seq_lens && o, "paged_attention: null pointer");
@@ -339,6 +354,21 @@ int sllm_paged_attention(const void* q, const void* k_cache, const void* v_cache
         p.part_lse = p.part_o + (int64_t)num_decoding_seqs * nq * p.num_splits * head_dim;
     }
     cudaStream_t st = (cudaStream_t)stream;
+    if (forced_generation() != 1 && tc_paged_supported(head_dim, block_size, nq, nkv, num_blocks, num_layers) &&
+        dtype <= SLLM_BF16) {
+        int e = launch_paged_tc(q, k_cache, v_cache, block_table, seq_ids, seq_lens, o, p.part_o, p.part_lse, p.scale_log2e,
+                                num_decoding_seqs, p.split_tokens, p.num_splits, cur_layer, num_layers, nq, nkv,
+                                max_blocks_per_seq, num_blocks, dtype, num_sms(), st);
+        if (e) return e;
+        if (p.num_splits > 1) {
+            dim3 g2(nq, num_decoding_seqs);
+            SLLM_DISPATCH_DTYPE(dtype, (paged_attn_merge_kernel<T><<<g2, head_dim, 0, st>>>(p.part_o, p.part_lse, (T*)o, seq_lens, nq,
+                                                                                          head_dim, p.num_splits, p.split_tokens)));
+            return check_launch("paged_attention(phase 2)");
+        }
+        return 0;
+    }
+    SLLM_REQUIRE(forced_generation() != 2, "paged_attention: SLLM_PAGED_ATTN_GEN=2 but the shape is not covered by the tcgen05 kernel");
     if (head_dim == 128) { SLLM_DISPATCH_DTYPE(dtype, return (launch_paged<T, 128>(p, num_decoding_seqs, max_seq_len, st))); }
     else { SLLM_DISPATCH_DTYPE(dtype, return (launch_paged<T, 64>(p, num_decoding_seqs, max_seq_len, st))); }
     return 0;
