@@ -1,0 +1,59 @@
+"""Times the UNMODIFIED reference (swiftLLM, installed into baseline/_ref by pip --target; git-ignored) on the GPU:
+its own Triton kernels + cuBLAS, fp16 as shipped, BASELINE config 2 (Llama-3-8B shapes, pure decode, batch 256,
+seq_len 4096).  Informational companion to bench.py (the contract's `--impl reference` arm is the CPU port):
+prints one JSON line with the reference's decode step time and the time of its paged_attention (phase 1 + 2)."""
+import json, os, statistics, sys, tempfile, types
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF = os.path.join(ROOT, "baseline", "_ref")
+if not os.path.isdir(os.path.join(REF, "swiftllm")):
+    print(json.dumps({"impl": "reference-triton", "unavailable": "baseline/_ref/swiftllm not installed"})); sys.exit(0)
+sys.path.insert(0, REF)
+import torch
+ray = types.ModuleType("ray"); ray.remote = lambda cls: cls; sys.modules["ray"] = ray
+try:
+    import flash_attn
+    sys.modules["vllm_flash_attn"] = flash_attn
+except Exception:
+    m = types.ModuleType("vllm_flash_attn"); m.flash_attn_varlen_func = None; sys.modules["vllm_flash_attn"] = m
+import swiftllm
+from swiftllm.worker.layers import transformer_layer as TL
+
+B = int(os.environ.get("REF_BATCH", 256)); S = int(os.environ.get("REF_SEQLEN", 4096)); STEPS = int(os.environ.get("REF_STEPS", 10))
+cfg = dict(model_type="llama", num_hidden_layers=32, num_attention_heads=32, num_key_value_heads=8, hidden_size=4096,
+           intermediate_size=14336, vocab_size=128256, max_position_embeddings=8192, rope_theta=500000.0, rms_norm_eps=1e-5,
+           hidden_act="silu")
+tmp = tempfile.mkdtemp(); json.dump(cfg, open(os.path.join(tmp, "config.json"), "w"))
+ec = swiftllm.EngineConfig(model_path=tmp, use_dummy=True, block_size=16, gpu_mem_utilization=0.97, num_cpu_blocks=1,
+                           max_seqs_in_block_table=B, max_blocks_per_seq=S // 16 + 8, max_batch_size=B, max_tokens_in_batch=8192)
+model = swiftllm.LlamaModel(ec)
+model.load_weights()
+nblk = B * (S // 16) + 64
+model.init_kvcache_and_swap(nblk)
+with torch.inference_mode():
+    g = torch.Generator(device="cuda"); g.manual_seed(1)
+    ch = max(1, nblk // 64)
+    for s in range(0, nblk, ch):
+        model.k_cache[s:s + ch].normal_(generator=g); model.v_cache[s:s + ch].normal_(generator=g)
+events = []
+orig = TL.paged_attention
+def timed_paged(*a, **k):
+    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    e0.record(); orig(*a, **k); e1.record(); events.append((e0, e1))
+TL.paged_attention = timed_paged
+ids = [[1]] * B; sids = list(range(B)); lens = [S] * B
+for _ in range(3):
+    model.forward(ids, sids, lens)
+events.clear()
+torch.cuda.synchronize()
+t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
+t0.record()
+for _ in range(STEPS):
+    model.forward(ids, sids, lens)
+t1.record(); torch.cuda.synchronize()
+ms = t0.elapsed_time(t1) / STEPS
+pa = statistics.mean(a.elapsed_time(b) for a, b in events)
+alg = B * S * 8 * 128 * 2 * 2 + 2 * B * 32 * 128 * 2
+print(json.dumps({"impl": "reference-triton", "dtype": "fp16 (as shipped)", "metric": "decode_tokens_per_s", "value": B / (ms * 1e-3),
+                  "ms_per_step": ms, "paged_attention_ms_per_layer": pa, "paged_attention_GBps_algorithmic": alg / (pa * 1e-3) / 1e9,
+                  "batch": B, "seq_len": S, "steps": STEPS, "triton": __import__("triton").__version__, "torch": torch.__version__}))
