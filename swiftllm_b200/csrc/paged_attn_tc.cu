@@ -30,14 +30,14 @@ using namespace tc;
 constexpr int TC_D = 128;
 constexpr int TC_BS = 16;                 // tokens per page
 constexpr int TC_TILE = 128;              // tokens per pipeline stage (8 pages)
-constexpr int TC_STAGES = 3;
-constexpr int TC_THREADS = 192;           // warp 0 producer, warp 1 MMA, warps 2..5 softmax
+constexpr int TC_KSTAGES = 3;             // K ring (freed as soon as S = K.Q^T of the tile has completed)
+constexpr int TC_VSTAGES = 3;             // V ring (freed when O = V^T.P^T of the tile has completed)
+constexpr int TC_THREADS = 224;           // warp 0: K+Q producer, warp 1: MMA issuer, warps 2..5: softmax, warp 6: V producer
 constexpr int TC_NPAD = 16;               // UMMA N (heads, padded)
-constexpr int TC_KV_STAGE_BYTES = 2 * TC_TILE * TC_D * 2;      // K + V = 64 KiB
-constexpr int TC_K_BYTES = TC_TILE * TC_D * 2;                 // 32 KiB
+constexpr int TC_K_BYTES = TC_TILE * TC_D * 2;                 // 32 KiB per K (or V) tile
 constexpr int TC_Q_BYTES = 2 * TC_NPAD * 128;                  // [half][16 rows][128 B] = 4 KiB
 constexpr int TC_P_BYTES = 2 * TC_NPAD * 128;                  // [token half][16 rows][128 B] = 4 KiB
-constexpr int TC_SMEM_BYTES = TC_STAGES * TC_KV_STAGE_BYTES + 2 * TC_Q_BYTES + 2 * TC_P_BYTES + 2048;
+constexpr int TC_SMEM_BYTES = (TC_KSTAGES + TC_VSTAGES) * TC_K_BYTES + 2 * TC_Q_BYTES + 2 * TC_P_BYTES + 2048;
 constexpr int TC_TMEM_COLS = 64;          // S: 2 x 16, O: 2 x 16
 
 struct TcParams {
@@ -45,12 +45,13 @@ struct TcParams {
     void* o; float* part_o; float* part_lse;
     float scale_log2e;
     int split_tokens, num_splits, cur_layer, num_layers, nq, nkv, max_blocks_per_seq, num_seqs, num_items;
-    // shared-memory placement of the 1 KiB atoms of a KV tile (see atom_off) and the matching descriptor strides
+    // shared-memory placement of the 1 KiB atoms of a KV tile and the matching descriptor strides
     int page_stride, tg_stride, half_stride, k_sbo, v_lbo, v_sbo, tma_4d;
 };
 
 struct Barriers {       // all mbarriers of the CTA (shared memory)
-    uint64_t kv_full[TC_STAGES], kv_empty[TC_STAGES];
+    uint64_t k_full[TC_KSTAGES], k_empty[TC_KSTAGES];
+    uint64_t v_full[TC_VSTAGES], v_empty[TC_VSTAGES];
     uint64_t q_full[2], q_empty[2];
     uint64_t s_full[2], s_empty[2];
     uint64_t p_full[2];
@@ -71,30 +72,109 @@ __device__ __forceinline__ bool get_item(const TcParams& p, int idx, Item& it) {
     return true;
 }
 
+// Walks this CTA's work items tile by tile (every role runs the same deterministic schedule).
+struct TileCursor {
+    int idx;            // global item index (blockIdx.x + k * gridDim.x)
+    Item it;
+    int j;              // tile within the item
+    uint32_t t, n;      // tile / item counters of this CTA
+    bool valid;
+    __device__ __forceinline__ void seek(const TcParams& p) {            // position on the next non-empty item
+        valid = false;
+        while (idx < p.num_items) {
+            if (get_item(p, idx, it)) { valid = true; j = 0; return; }
+            idx += gridDim.x;
+        }
+    }
+    __device__ __forceinline__ void init(const TcParams& p) { idx = blockIdx.x; t = 0; n = 0; seek(p); }
+    __device__ __forceinline__ void advance(const TcParams& p) {
+        t++;
+        if (++j == it.ntiles) { n++; idx += gridDim.x; seek(p); }
+    }
+};
+
+// One producer warp streams either the K or the V tiles (plus Q when IS_K): 32 block-table entries are fetched per
+// 4 tiles (prefetched one group ahead), lanes 0..7 each issue the TMA of one page.
+template <bool IS_K>
+__device__ __forceinline__ void producer_loop(const TcParams& p, const CUtensorMap* map, const CUtensorMap* qmap, uint8_t* ring,
+                                              uint64_t* full, uint64_t* empty, int nstages, Barriers* bars, uint8_t* q_sm, int g, int lane) {
+    uint32_t t = 0, n = 0;
+    for (int idx = blockIdx.x; idx < p.num_items; idx += gridDim.x) {
+        Item it;
+        if (!get_item(p, idx, it)) continue;
+        if (IS_K) {       // Q of this item: rows [seq*nq + kvh*g, +16) x 128 d as two 64-wide boxes
+            const int qb = n & 1;
+            if (lane == 0) {
+                mbar_wait(smem_u32(&bars->q_empty[qb]), ((n >> 1) & 1) ^ 1);
+                const uint32_t qbar = smem_u32(&bars->q_full[qb]);
+                mbar_arrive_expect_tx(qbar, TC_Q_BYTES);
+                const int row = it.seq * p.nq + it.kvh * g;
+                tma_load_2d(smem_u32(q_sm + qb * TC_Q_BYTES), qmap, qbar, 0, row);
+                tma_load_2d(smem_u32(q_sm + qb * TC_Q_BYTES + 2048), qmap, qbar, 64, row);
+            }
+        }
+        const int first_page = it.split_start / TC_BS;
+        const int npages = (it.split_len + TC_BS - 1) / TC_BS;
+        const int32_t* bt = p.block_table + (int64_t)p.seq_ids[it.seq] * p.max_blocks_per_seq + first_page;
+        int next_blk = lane < npages ? bt[lane] : 0;                       // group 0
+        for (int tile0 = 0; tile0 < it.ntiles; tile0 += 4) {
+            const int my_blk = next_blk;
+            const int npg = (tile0 + 4) * 8 + lane;                        // prefetch the next group's entries
+            next_blk = (tile0 + 4 < it.ntiles && npg < npages) ? bt[npg] : 0;
+            const int nt = min(4, it.ntiles - tile0);
+            for (int j = 0; j < nt; j++, t++) {
+                const int stage = t % nstages;
+                const int valid = min(8, npages - (tile0 + j) * 8);
+                const uint32_t bar = smem_u32(&full[stage]);
+                if (lane == 0) {
+                    mbar_wait(smem_u32(&empty[stage]), ((t / nstages) & 1) ^ 1);
+                    mbar_arrive_expect_tx(bar, (uint32_t)valid * TC_BS * TC_D * 2);
+                }
+                __syncwarp();
+                const int blk = __shfl_sync(0xffffffffu, my_blk, j * 8 + (lane & 7));
+                if (lane < valid) {
+                    // row of the cache viewed as [num_blocks*L*nkv*16 rows, 128]: first token row of this page
+                    const int64_t row = (((int64_t)blk * p.num_layers + p.cur_layer) * p.nkv + it.kvh) * TC_BS;
+                    const uint32_t dst = smem_u32(ring + stage * TC_K_BYTES) + lane * p.page_stride;
+                    if (p.tma_4d) {
+                        tma_load_4d(dst, map, bar, 0, 0, 0, (int)(row >> 3));
+                    } else {
+                        tma_load_2d(dst, map, bar, 0, (int)row);
+                        tma_load_2d(dst + p.half_stride, map, bar, 64, (int)row);
+                    }
+                }
+            }
+        }
+        n++;
+    }
+}
+
 template <typename T, int G>      // G = number of S/O columns read back (GQA group padded to 4, 8 or 16)
 __global__ void __launch_bounds__(TC_THREADS, 1) paged_attn_tc_kernel(const __grid_constant__ CUtensorMap kmap,
                                                                       const __grid_constant__ CUtensorMap vmap,
                                                                       const __grid_constant__ CUtensorMap qmap,
                                                                       const TcParams p) {
     extern __shared__ __align__(1024) uint8_t smem[];
-    uint8_t* kv_sm = smem;                                           // [stage][K 32 KiB | V 32 KiB]
-    uint8_t* q_sm = smem + TC_STAGES * TC_KV_STAGE_BYTES;            // [2][4 KiB]
+    uint8_t* k_sm = smem;                                            // [KSTAGES][32 KiB]
+    uint8_t* v_sm = smem + TC_KSTAGES * TC_K_BYTES;                  // [VSTAGES][32 KiB]
+    uint8_t* q_sm = v_sm + TC_VSTAGES * TC_K_BYTES;                  // [2][4 KiB]
     uint8_t* p_sm = q_sm + 2 * TC_Q_BYTES;                           // [2][4 KiB]
     uint8_t* misc = p_sm + 2 * TC_P_BYTES;                           // barriers, tmem base, reduction scratch
     Barriers* bars = reinterpret_cast<Barriers*>(misc);
     uint32_t* tmem_base_s = reinterpret_cast<uint32_t*>(misc + 256);
-    float* red = reinterpret_cast<float*>(misc + 320);               // [2 parity][4 warps][16 heads] = 512 B
+    float* red = reinterpret_cast<float*>(misc + 320);               // [2 parity][4 warps][16] + [4][16] sums
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int g = p.nq / p.nkv;
 
     // ---- one-time setup
-    {   // zero the KV ring: page slots that a short tail tile never loads must hold finite data (P = 0 there)
-        uint4* z = reinterpret_cast<uint4*>(kv_sm);
-        for (int i = tid; i < TC_STAGES * TC_KV_STAGE_BYTES / 16; i += TC_THREADS) z[i] = make_uint4(0, 0, 0, 0);
+    {   // zero the V ring (and K): page slots that a short tail tile never loads must hold finite data (P = 0 there)
+        uint4* z = reinterpret_cast<uint4*>(smem);
+        for (int i = tid; i < (TC_KSTAGES + TC_VSTAGES) * TC_K_BYTES / 16; i += TC_THREADS) z[i] = make_uint4(0, 0, 0, 0);
     }
     if (tid == 0) {
-        for (int i = 0; i < TC_STAGES; i++) { mbar_init(smem_u32(&bars->kv_full[i]), 1); mbar_init(smem_u32(&bars->kv_empty[i]), 1); }
+        for (int i = 0; i < TC_KSTAGES; i++) { mbar_init(smem_u32(&bars->k_full[i]), 1); mbar_init(smem_u32(&bars->k_empty[i]), 1); }
+        for (int i = 0; i < TC_VSTAGES; i++) { mbar_init(smem_u32(&bars->v_full[i]), 1); mbar_init(smem_u32(&bars->v_empty[i]), 1); }
         for (int i = 0; i < 2; i++) {
             mbar_init(smem_u32(&bars->q_full[i]), 1); mbar_init(smem_u32(&bars->q_empty[i]), 1);
             mbar_init(smem_u32(&bars->s_full[i]), 1); mbar_init(smem_u32(&bars->s_empty[i]), 128);
@@ -112,107 +192,65 @@ __global__ void __launch_bounds__(TC_THREADS, 1) paged_attn_tc_kernel(const __gr
     const uint32_t tmem = *tmem_base_s;
 
     if (warp == 0) {
-        // =========================================================== TMA producer (whole warp converged, lane 0 issues)
-        uint32_t t = 0, n = 0;                      // global tile / item counters of this CTA
-        for (int idx = blockIdx.x; idx < p.num_items; idx += gridDim.x) {
-            Item it;
-            if (!get_item(p, idx, it)) continue;
-            // Q of this item: rows [seq*nq + kvh*g, +16) x 128 d as two 64-wide boxes
-            const int qb = n & 1;
-            if (lane == 0) {
-                mbar_wait(smem_u32(&bars->q_empty[qb]), ((n >> 1) & 1) ^ 1);
-                const uint32_t qbar = smem_u32(&bars->q_full[qb]);
-                mbar_arrive_expect_tx(qbar, TC_Q_BYTES);
-                const int row = it.seq * p.nq + it.kvh * g;
-                tma_load_2d(smem_u32(q_sm + qb * TC_Q_BYTES), &qmap, qbar, 0, row);
-                tma_load_2d(smem_u32(q_sm + qb * TC_Q_BYTES + 2048), &qmap, qbar, 64, row);
-            }
-            const int first_page = it.split_start / TC_BS;
-            const int npages = (it.split_len + TC_BS - 1) / TC_BS;
-            const int32_t* bt = p.block_table + (int64_t)p.seq_ids[it.seq] * p.max_blocks_per_seq + first_page;
-            for (int tile0 = 0; tile0 < it.ntiles; tile0 += 4) {         // 32 block-table entries per outer iteration
-                const int pg = tile0 * 8 + lane;
-                const int my_blk = pg < npages ? bt[pg] : 0;
-                const int nt = min(4, it.ntiles - tile0);
-                for (int j = 0; j < nt; j++, t++) {
-                    const int stage = t % TC_STAGES;
-                    const int valid = min(8, npages - (tile0 + j) * 8);
-                    if (lane == 0) mbar_wait(smem_u32(&bars->kv_empty[stage]), ((t / TC_STAGES) & 1) ^ 1);
-                    __syncwarp();
-                    const uint32_t bar = smem_u32(&bars->kv_full[stage]);
-                    if (lane == 0) mbar_arrive_expect_tx(bar, (uint32_t)valid * 2 * TC_BS * TC_D * 2);
-#pragma unroll
-                    for (int pi = 0; pi < 8; pi++) {
-                        const int blk = __shfl_sync(0xffffffffu, my_blk, j * 8 + pi);
-                        if (pi < valid && lane == 0) {
-                            // row of the cache viewed as [num_blocks*L*nkv*16 rows, 128]: first token row of this page
-                            const int64_t row = (((int64_t)blk * p.num_layers + p.cur_layer) * p.nkv + it.kvh) * TC_BS;
-                            const uint32_t kdst = smem_u32(kv_sm + stage * TC_KV_STAGE_BYTES) + pi * p.page_stride;
-                            const uint32_t vdst = kdst + TC_K_BYTES;
-                            if (p.tma_4d) {
-                                tma_load_4d(kdst, &kmap, bar, 0, 0, 0, (int)(row >> 3));
-                                tma_load_4d(vdst, &vmap, bar, 0, 0, 0, (int)(row >> 3));
-                            } else {
-                                tma_load_2d(kdst, &kmap, bar, 0, (int)row);
-                                tma_load_2d(kdst + p.half_stride, &kmap, bar, 64, (int)row);
-                                tma_load_2d(vdst, &vmap, bar, 0, (int)row);
-                                tma_load_2d(vdst + p.half_stride, &vmap, bar, 64, (int)row);
-                            }
-                        }
-                    }
-                }
-            }
-            n++;
-        }
+        producer_loop<true>(p, &kmap, &qmap, k_sm, bars->k_full, bars->k_empty, TC_KSTAGES, bars, q_sm, g, lane);
+    } else if (warp == 6) {
+        producer_loop<false>(p, &vmap, &qmap, v_sm, bars->v_full, bars->v_empty, TC_VSTAGES, bars, q_sm, g, lane);
     } else if (warp == 1) {
-        // =========================================================== MMA issuer (lane 0)
+        // =========================================================== MMA issuer (lane 0): two in-order queues, polled
         if (lane == 0) {
             constexpr uint32_t IDESC_S = make_instr_desc(128, TC_NPAD, UmmaFmt<T>::value, 0, 0);   // A K-major, B K-major
             constexpr uint32_t IDESC_O = make_instr_desc(128, TC_NPAD, UmmaFmt<T>::value, 1, 0);   // A MN-major (V^T)
-            uint32_t t = 0, n = 0;
-            int pend_stage = -1, pend_b = 0;            // PV of the previous tile is issued after S of the current one
-            uint32_t pend_t = 0;
-            auto issue_pv = [&](int stage, int b, uint32_t tt) {
-                mbar_wait(smem_u32(&bars->p_full[b]), (tt >> 1) & 1);
-                mbar_wait(smem_u32(&bars->o_empty[b]), ((tt >> 1) & 1) ^ 1);
-                tc_fence_after();
-                const uint32_t vbase = smem_u32(kv_sm + stage * TC_KV_STAGE_BYTES + TC_K_BYTES);
-                const uint32_t pbase = smem_u32(p_sm + b * TC_P_BYTES);
+            TileCursor cs, cp;                  // next S tile / next PV tile
+            cs.init(p); cp.init(p);
+            uint32_t spins = 0;
+            while (cp.valid) {
+                bool progressed = false;
+                if (cs.valid) {
+                    const uint32_t t = cs.t;
+                    const int stage = t % TC_KSTAGES, b = t & 1, qb = cs.n & 1;
+                    if ((cs.j > 0 || mbar_test_wait(smem_u32(&bars->q_full[qb]), (cs.n >> 1) & 1)) &&
+                        mbar_test_wait(smem_u32(&bars->k_full[stage]), (t / TC_KSTAGES) & 1) &&
+                        mbar_test_wait(smem_u32(&bars->s_empty[b]), ((t >> 1) & 1) ^ 1)) {
+                        tc_fence_after();
+                        const uint32_t kbase = smem_u32(k_sm + stage * TC_K_BYTES);
+                        const uint32_t qbase = smem_u32(q_sm + qb * TC_Q_BYTES);
 #pragma unroll
-                for (int kt = 0; kt < 8; kt++) {        // 16 tokens (one page) per UMMA
-                    const uint64_t a = make_smem_desc(vbase + kt * p.page_stride, p.v_lbo, p.v_sbo);
-                    const uint64_t bd = make_smem_desc(pbase + (kt >> 2) * 2048 + (kt & 3) * 32, 16, 1024);
-                    umma_ss(tmem + 32 + b * 16, a, bd, IDESC_O, kt > 0);
-                }
-                umma_commit(smem_u32(&bars->o_full[b]));
-                umma_commit(smem_u32(&bars->kv_empty[stage]));
-            };
-            for (int idx = blockIdx.x; idx < p.num_items; idx += gridDim.x) {
-                Item it;
-                if (!get_item(p, idx, it)) continue;
-                const int qb = n & 1;
-                mbar_wait(smem_u32(&bars->q_full[qb]), (n >> 1) & 1);
-                const uint32_t qbase = smem_u32(q_sm + qb * TC_Q_BYTES);
-                for (int j = 0; j < it.ntiles; j++, t++) {
-                    const int stage = t % TC_STAGES, b = t & 1;
-                    mbar_wait(smem_u32(&bars->kv_full[stage]), (t / TC_STAGES) & 1);
-                    mbar_wait(smem_u32(&bars->s_empty[b]), ((t >> 1) & 1) ^ 1);
-                    tc_fence_after();
-                    const uint32_t kbase = smem_u32(kv_sm + stage * TC_KV_STAGE_BYTES);
-#pragma unroll
-                    for (int ks = 0; ks < 8; ks++) {    // 16 d per UMMA; d-half = ks / 4
-                        const uint64_t a = make_smem_desc(kbase + (ks >> 2) * p.half_stride + (ks & 3) * 32, 16, p.k_sbo);
-                        const uint64_t bd = make_smem_desc(qbase + (ks >> 2) * 2048 + (ks & 3) * 32, 16, 1024);
-                        umma_ss(tmem + b * 16, a, bd, IDESC_S, ks > 0);
+                        for (int ks = 0; ks < 8; ks++) {    // 16 d per UMMA; d-half = ks / 4
+                            const uint64_t a = make_smem_desc(kbase + (ks >> 2) * p.half_stride + (ks & 3) * 32, 16, p.k_sbo);
+                            const uint64_t bd = make_smem_desc(qbase + (ks >> 2) * 2048 + (ks & 3) * 32, 16, 1024);
+                            umma_ss(tmem + b * 16, a, bd, IDESC_S, ks > 0);
+                        }
+                        umma_commit(smem_u32(&bars->s_full[b]));
+                        umma_commit(smem_u32(&bars->k_empty[stage]));                       // K tile consumed
+                        if (cs.j == cs.it.ntiles - 1) umma_commit(smem_u32(&bars->q_empty[qb]));   // Q buffer reusable
+                        cs.advance(p);
+                        progressed = true;
                     }
-                    umma_commit(smem_u32(&bars->s_full[b]));
-                    if (j == it.ntiles - 1) umma_commit(smem_u32(&bars->q_empty[qb]));     // Q buffer reusable
-                    if (pend_stage >= 0) issue_pv(pend_stage, pend_b, pend_t);
-                    pend_stage = stage; pend_b = b; pend_t = t;
                 }
-                n++;
+                if (cp.t < cs.t || !cs.valid) {
+                    const uint32_t t = cp.t;
+                    const int stage = t % TC_VSTAGES, b = t & 1;
+                    if (mbar_test_wait(smem_u32(&bars->p_full[b]), (t >> 1) & 1) &&
+                        mbar_test_wait(smem_u32(&bars->v_full[stage]), (t / TC_VSTAGES) & 1) &&
+                        mbar_test_wait(smem_u32(&bars->o_empty[b]), ((t >> 1) & 1) ^ 1)) {
+                        tc_fence_after();
+                        const uint32_t vbase = smem_u32(v_sm + stage * TC_K_BYTES);
+                        const uint32_t pbase = smem_u32(p_sm + b * TC_P_BYTES);
+#pragma unroll
+                        for (int kt = 0; kt < 8; kt++) {        // 16 tokens (one page) per UMMA
+                            const uint64_t a = make_smem_desc(vbase + kt * p.page_stride, p.v_lbo, p.v_sbo);
+                            const uint64_t bd = make_smem_desc(pbase + (kt >> 2) * 2048 + (kt & 3) * 32, 16, 1024);
+                            umma_ss(tmem + 32 + b * 16, a, bd, IDESC_O, kt > 0);
+                        }
+                        umma_commit(smem_u32(&bars->o_full[b]));
+                        umma_commit(smem_u32(&bars->v_empty[stage]));
+                        cp.advance(p);
+                        progressed = true;
+                    }
+                }
+                if (progressed) spins = 0;
+                else if (++spins > (1u << 24)) { printf("sllm: MMA issuer watchdog (block %d, S tile %u, PV tile %u)\n", blockIdx.x, cs.t, cp.t); __trap(); }
             }
-            if (pend_stage >= 0) issue_pv(pend_stage, pend_b, pend_t);
         }
     } else {
         // =========================================================== softmax / accumulate warps (128 threads)
@@ -273,10 +311,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) paged_attn_tc_kernel(const __gr
                     const float a = fast_exp2_tc(m_run[h] - mn);
                     pj[h] = fast_exp2_tc(x[h] - mn);
                     l_part[h] = l_part[h] * a + pj[h];
-                    // the previous tile's O (relative to the old max) is folded below with alpha_prev; chain the
-                    // correction: after folding O(j-1) acc is relative to m(j-1); this tile's factor applies when O(j) folds
                     m_run[h] = mn;
-                    x[h] = a;                                              // reuse x[] to carry alpha(j)
+                    x[h] = a;                                              // x[] now carries alpha(j) = exp2(m(j-1) - m(j))
                 }
                 // P^T tile (B operand of the PV UMMA): [token half][16 head rows][128 B], SWIZZLE_128B.
                 // Buffer b was last read by PV(t-2), whose completion (o_full) these threads observed last iteration.
@@ -329,6 +365,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) paged_attn_tc_kernel(const __gr
     __syncthreads();
     if (warp == 1) tmem_dealloc<TC_TMEM_COLS>(tmem);
 }
+
+}  // namespace sllm
+
+namespace sllm {
 
 // ------------------------------------------------------------------ host side
 namespace {

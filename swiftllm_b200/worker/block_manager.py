@@ -81,7 +81,10 @@ class BlockManager:
         if not sids:
             return
         idx = np.asarray(sids, dtype=np.int64)
-        self.num_free_blocks += int(self._host_nsab[idx].sum())
+        total = int(self._host_nsab[idx].sum())
+        if total == 0:
+            return                      # nothing allocated for these sequences on this device
+        self.num_free_blocks += total
         self._host_nsab[idx] = 0
         unset_block_table_and_num_seq_alloc_blocks(self.num_seq_allocated_blocks, self.block_table,
                                                    seq_ids.to(torch.int32), self.is_block_free)
