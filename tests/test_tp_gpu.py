@@ -1,0 +1,88 @@
+"""GPU (needs >= 2 devices; skipped otherwise): tensor-parallel LlamaModel (heads / FFN columns sharded, one NCCL
+all-reduce after o_proj and down_proj) against the TP=1 model on the same synthetic weights: identical KV-block
+indices, greedy tokens equal where the top-1 margin is clear, logits within bf16 tolerance."""
+import os
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+CFG = dict(model_type="llama", num_hidden_layers=3, num_attention_heads=8, num_key_value_heads=4, hidden_size=1024,
+           vocab_size=1000, max_position_embeddings=512, intermediate_size=1536, rope_theta=500000.0, rms_norm_eps=1e-5,
+           hidden_act="silu")
+
+
+def _run(rank, world, port, q):
+    import numpy as np
+    import torch.distributed as dist
+    import swiftllm_b200
+    from swiftllm_b200.worker.weight import synthetic_getter
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+
+    def make(tp, r, graph=False):
+        ec = swiftllm_b200.EngineConfig(model_path="", use_dummy=False, block_size=16, gpu_mem_utilization=0.9, num_cpu_blocks=2,
+                                        max_seqs_in_block_table=8, max_blocks_per_seq=16, max_batch_size=4, max_tokens_in_batch=256,
+                                        dtype="bfloat16", tp_size=tp, tp_rank=r, use_cuda_graph=graph)
+        m = swiftllm_b200.LlamaModel(ec, swiftllm_b200.LlamaModelConfig(CFG))
+        m.load_weights(synthetic_getter(seed=11, std=0.05, device=f"cuda:{rank}"))
+        m.init_kvcache_and_swap(40)
+        m.post_layer.keep_logits = True
+        return m
+    tp = make(world, rank)
+    tpg = make(world, rank, graph=True)
+    ref = make(1, 0) if rank == 0 else None
+    rng = np.random.default_rng(3)
+    prompts = [rng.integers(0, 1000, size=n).tolist() for n in (40, 7, 129)]
+    sids = [5, 0, 2]
+    worst = 0.0
+    toks = tp.forward(prompts, sids, []); tg = tpg.forward(prompts, sids, [])
+    assert toks == tg
+    lens = [len(p) for p in prompts]
+    rt = ref.forward(prompts, sids, []) if ref else None
+    for step in range(6):
+        if ref:
+            a, b = tp.post_layer.last_logits.float(), ref.post_layer.last_logits.float()
+            rel = float((a - b).abs().max() / b.abs().max()); worst = max(worst, rel)
+            top2 = b.topk(2, dim=1).values
+            clear = ((top2[:, 0] - top2[:, 1]) > 2 * 2 ** -5 * b.abs().max()).tolist()
+            assert rel <= 2 ** -5, rel
+            for x, y, c in zip(toks, rt, clear):
+                if c:
+                    assert x == y
+            n = ref.gpu_block_manager.num_seq_allocated_blocks
+            assert torch.equal(tp.gpu_block_manager.num_seq_allocated_blocks, n)
+            for s in sids:
+                k = int(n[s])
+                assert torch.equal(tp.gpu_block_manager.block_table[s, :k], ref.gpu_block_manager.block_table[s, :k])
+        # all ranks must feed the same tokens: use rank 0's reference tokens
+        feed = [rt if ref else None]
+        dist.broadcast_object_list(feed, src=0)
+        lens = [l + 1 for l in lens]
+        ids = [[t] for t in feed[0]]
+        toks = tp.forward(ids, sids, lens); tg = tpg.forward(ids, sids, lens)
+        assert toks == tg                                  # CUDA-graph decode with NCCL inside == eager
+        if ref:
+            rt = ref.forward(ids, sids, lens)
+    if rank == 0:
+        q.put(worst)
+    dist.barrier(); dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_tp_matches_single_gpu(world):
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs")
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_run, args=(r, world, 29650 + world, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    worst = q.get(timeout=600)
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    assert worst <= 2 ** -5
