@@ -305,6 +305,14 @@ def run_ours(args):
     else:
         peak, peak_src = 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
     achieved = alg_bytes / (pa_ms * 1e-3) / 1e9
+    traffic, traffic_src = None, None
+    tpath = os.path.join(ROOT, "profiles", "paged_attn_traffic.json")
+    if os.path.exists(tpath) and n == 1 and args.model == "llama3-8b" and B == 256 and S == 4096 and not args.layers:
+        tj = json.load(open(tpath))
+        traffic, traffic_src = tj["dram_bytes_read"] + tj["dram_bytes_write"], tj["source"]
+    gen = os.environ.get("SLLM_PAGED_ATTN_GEN", "")
+    kname = "paged_attn_kernel (gen 1: cp.async + mma.sync)" if gen == "1" else \
+        "paged_attn_tc_kernel (gen 2: tcgen05 + TMA, persistent)"
 
     # ---- optional: prefill tokens/s (secondary metric of BASELINE.json)
     prefill = None
@@ -326,8 +334,7 @@ def run_ours(args):
             prefill = {"error": str(e)[:200]}
 
     if rank != 0:
-        if n > 1:
-            dist.barrier(); dist.destroy_process_group()
+        _finish_distributed(model, n)
         return
 
     cpu = None
@@ -345,8 +352,8 @@ def run_ours(args):
         "gpu_launches": launches_per_step * args.steps,
         "gpu_launches_note": f"{launches_per_step} native (libswiftllm_b200.so) launch calls per decode step "
                              f"({'replayed from a CUDA graph' if graph is not None else 'eager'}); GEMMs/embedding/argmax are library calls on top",
-        "roofline": {"kernel": "paged_attn_kernel (decode attention)", "bound": "hbm", "achieved": achieved, "peak": peak,
-                     "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+        "roofline": {"kernel": kname, "bound": "hbm", "achieved": achieved, "peak": peak,
+                     "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": alg_bytes, "mean_launch_ms": pa_ms, "launches_timed": len(durs),
                      "how": "CUDA events around every paged_attention launch over K eager decode steps on the launching stream"},
         "clocks": clk,
@@ -356,8 +363,21 @@ def run_ours(args):
     if args.layers:
         line["reduced"] = "layer count overridden: NOT a valid BASELINE measurement"
     print(json.dumps(line), flush=True)
-    if n > 1:
-        dist.barrier(); dist.destroy_process_group()
+    _finish_distributed(model, n)
+
+
+def _finish_distributed(model, n):
+    """Leave a multi-rank run without hanging: NCCL kernels captured in live CUDA graphs make
+    destroy_process_group() block, so drop the graphs, synchronise, rendezvous once and hard-exit."""
+    if n <= 1:
+        return
+    import torch.distributed as dist
+    model._graphs.clear()
+    torch.cuda.synchronize()
+    dist.barrier()
+    torch.cuda.synchronize()
+    sys.stdout.flush(); sys.stderr.flush()
+    os._exit(0)
 
 
 def main():

@@ -68,7 +68,11 @@ def _run(rank, world, port, q):
             rt = ref.forward(ids, sids, lens)
     if rank == 0:
         q.put(worst)
-    dist.barrier(); dist.destroy_process_group()
+    # NCCL kernels captured in live CUDA graphs make destroy_process_group() block: drop the graphs and hard-exit
+    tpg._graphs.clear(); torch.cuda.synchronize(); dist.barrier(); torch.cuda.synchronize()
+    import time
+    time.sleep(0.5)            # let the parent drain the queue
+    os._exit(0)
 
 
 @pytest.mark.parametrize("world", [2, 4])
@@ -81,8 +85,10 @@ def test_tp_matches_single_gpu(world):
     procs = [ctx.Process(target=_run, args=(r, world, 29650 + world, q)) for r in range(world)]
     for p in procs:
         p.start()
-    worst = q.get(timeout=600)
+    worst = q.get(timeout=300)
     for p in procs:
-        p.join(timeout=120)
+        p.join(timeout=60)
+        if p.exitcode is None:
+            p.kill()
         assert p.exitcode == 0
     assert worst <= 2 ** -5
