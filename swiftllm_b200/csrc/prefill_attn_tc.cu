@@ -1,0 +1,372 @@
+// Causal varlen prefill attention, generation 2: tcgen05 + TMA, two query tiles per CTA in ping-pong (sm_100a).
+//
+// Reference being replaced: swiftllm/worker/kernels/prefill_attn.py:9-139 and the flash_attn_varlen_func call at
+// swiftllm/worker/layers/transformer_layer.py:86-96.  head_dim 128, fp16/bf16; numerics per SURVEY.md Appendix A6
+// (fp32 scores, exp2 online softmax in fp32, P rounded to the storage dtype before P.V, o = h(acc / l)).
+//
+// CTA = (sequence, q head, 256 query rows) = two 128-row tiles A and B.  320 threads:
+//   warp 0      TMA producer: Q (4 boxes of 128 rows x 64 d) once, then per 64-token step one K tile and one V tile
+//               (2 boxes of 64 x 64 each) into 2-stage rings, K and V on separate mbarriers.
+//   warp 1      MMA issuer (one thread, polling):  S_X[128 x 64] = Q_X . K_j^T       (8 UMMAs, M=128 N=64 K=16)
+//                                                   O_X[128 x 128] += P_X . V_j       (4 UMMAs, M=128 N=128 K=16, B MN-major)
+//               S_A, S_B (64 TMEM columns each) and O_A, O_B (128 columns each) live in TMEM.
+//   warps 2-5   softmax of tile A, warps 6-9 softmax of tile B: thread = query row = TMEM lane.  Row max and row sum
+//               are thread-local (no shuffles); P (storage dtype) goes to shared memory as the A operand of the PV
+//               UMMA; O is rescaled in TMEM only when the running max grew by more than 2^8 ("lazy rescale": the
+//               reference point m_ref trails the true max, exact in the end because l uses the same reference).
+// While one tile's softmax runs on the CUDA cores the tensor pipe works on the other tile.
+// Roofline: tensor-bound; FLOPs = 4 * nq * D * sum_i L_i (L_i + 1) / 2.
+#include <mutex>
+#include <unordered_map>
+
+#include "tc_helpers.cuh"
+
+namespace sllm {
+
+using namespace tc;
+
+constexpr int PT_D = 128;
+constexpr int PT_BQ = 128;                // rows per query tile (two tiles per CTA)
+constexpr int PT_BK = 64;                 // kv tokens per pipeline step
+constexpr int PT_STAGES = 2;
+constexpr int PT_THREADS = 320;
+constexpr int PT_Q_BYTES = PT_BQ * PT_D * 2;          // 32 KiB per query tile ([half][128 rows][128 B])
+constexpr int PT_KV_BYTES = PT_BK * PT_D * 2;         // 16 KiB per K (or V) tile ([half][64 rows][128 B])
+constexpr int PT_P_BYTES = PT_BQ * PT_BK * 2;         // 16 KiB per P tile ([128 rows][128 B])
+constexpr int PT_SMEM_BYTES = 2 * PT_Q_BYTES + 2 * PT_STAGES * PT_KV_BYTES + 2 * PT_P_BYTES + 1024;
+constexpr int PT_TMEM_COLS = 512;         // S_A 0..63, S_B 64..127, O_A 128..255, O_B 256..383
+constexpr float PT_RESCALE_THRESHOLD = 8.0f;          // log2 units
+
+struct PtBarriers {
+    uint64_t q_full;
+    uint64_t k_full[PT_STAGES], k_empty[PT_STAGES], v_full[PT_STAGES], v_empty[PT_STAGES];
+    uint64_t s_full[2], s_empty[2], p_full[2], p_empty[2];
+};
+
+struct PtParams {
+    void* o;
+    const int32_t* start_locs; const int32_t* seq_lens;
+    float scale_log2e;
+    int nq, nkv;
+};
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+                   "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+                   "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+                   "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+                 : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,%32};"
+                 :: "r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+                    "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]),
+                    "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]),
+                    "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+template <typename T>
+__global__ void __launch_bounds__(PT_THREADS, 1) prefill_attn_tc_kernel(const __grid_constant__ CUtensorMap qmap,
+                                                                        const __grid_constant__ CUtensorMap kmap,
+                                                                        const __grid_constant__ CUtensorMap vmap,
+                                                                        const PtParams p) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint8_t* q_sm = smem;                                       // [2 tiles][2 halves][128 rows][128 B]
+    uint8_t* k_sm = q_sm + 2 * PT_Q_BYTES;                      // [stage][2 halves][64 rows][128 B]
+    uint8_t* v_sm = k_sm + PT_STAGES * PT_KV_BYTES;
+    uint8_t* p_sm = v_sm + PT_STAGES * PT_KV_BYTES;             // [2 tiles][128 rows][128 B]
+    uint8_t* misc = p_sm + 2 * PT_P_BYTES;
+    PtBarriers* bars = reinterpret_cast<PtBarriers*>(misc);
+    uint32_t* tmem_base_s = reinterpret_cast<uint32_t*>(misc + 512);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int qblk = gridDim.x - 1 - blockIdx.x;                // latest (heaviest) query blocks first
+    const int head = blockIdx.y, seq = blockIdx.z;
+    const int len = p.seq_lens[seq];
+    const int q0 = qblk * 2 * PT_BQ;
+    if (q0 >= len) return;
+    const int tok0 = p.start_locs[seq];
+    const int kvh = head / (p.nq / p.nkv);
+    const bool active_b = q0 + PT_BQ < len;
+    const int nkt_a = (min(len, q0 + PT_BQ) + PT_BK - 1) / PT_BK;           // kv steps tile A takes part in
+    const int nkt_b = active_b ? (min(len, q0 + 2 * PT_BQ) + PT_BK - 1) / PT_BK : 0;
+    const int nkt = max(nkt_a, nkt_b);
+
+    if (tid == 0) {
+        mbar_init(smem_u32(&bars->q_full), 1);
+        for (int i = 0; i < PT_STAGES; i++) {
+            mbar_init(smem_u32(&bars->k_full[i]), 1); mbar_init(smem_u32(&bars->k_empty[i]), 1);
+            mbar_init(smem_u32(&bars->v_full[i]), 1); mbar_init(smem_u32(&bars->v_empty[i]), 1);
+        }
+        for (int i = 0; i < 2; i++) {
+            mbar_init(smem_u32(&bars->s_full[i]), 1); mbar_init(smem_u32(&bars->s_empty[i]), 128);
+            mbar_init(smem_u32(&bars->p_full[i]), 128); mbar_init(smem_u32(&bars->p_empty[i]), 1);
+        }
+        mbar_fence_init();
+        tma_prefetch_desc(&qmap); tma_prefetch_desc(&kmap); tma_prefetch_desc(&vmap);
+    }
+    if (warp == 1) tmem_alloc<PT_TMEM_COLS>(smem_u32(tmem_base_s));
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_base_s;
+
+    if (warp == 0) {
+        // =========================================================== TMA producer
+        if (lane == 0) {
+            const uint32_t qbar = smem_u32(&bars->q_full);
+            mbar_arrive_expect_tx(qbar, 2 * PT_Q_BYTES);
+            for (int x = 0; x < 2; x++)
+                for (int h = 0; h < 2; h++)
+                    tma_load_2d(smem_u32(q_sm + x * PT_Q_BYTES + h * (PT_Q_BYTES / 2)), &qmap, qbar, head * PT_D + h * 64,
+                                tok0 + q0 + x * PT_BQ);
+            for (int j = 0; j < nkt; j++) {
+                const int st = j % PT_STAGES;
+                const uint32_t par = ((j / PT_STAGES) & 1) ^ 1;
+                mbar_wait(smem_u32(&bars->k_empty[st]), par);
+                const uint32_t kb = smem_u32(&bars->k_full[st]);
+                mbar_arrive_expect_tx(kb, PT_KV_BYTES);
+                tma_load_2d(smem_u32(k_sm + st * PT_KV_BYTES), &kmap, kb, kvh * PT_D, tok0 + j * PT_BK);
+                tma_load_2d(smem_u32(k_sm + st * PT_KV_BYTES + PT_KV_BYTES / 2), &kmap, kb, kvh * PT_D + 64, tok0 + j * PT_BK);
+                mbar_wait(smem_u32(&bars->v_empty[st]), par);
+                const uint32_t vb = smem_u32(&bars->v_full[st]);
+                mbar_arrive_expect_tx(vb, PT_KV_BYTES);
+                tma_load_2d(smem_u32(v_sm + st * PT_KV_BYTES), &vmap, vb, kvh * PT_D, tok0 + j * PT_BK);
+                tma_load_2d(smem_u32(v_sm + st * PT_KV_BYTES + PT_KV_BYTES / 2), &vmap, vb, kvh * PT_D + 64, tok0 + j * PT_BK);
+            }
+        }
+    } else if (warp == 1) {
+        // =========================================================== MMA issuer (one thread, polling three queues)
+        if (lane == 0) {
+            constexpr uint32_t IDESC_S = make_instr_desc(128, PT_BK, UmmaFmt<T>::value, 0, 0);
+            constexpr uint32_t IDESC_O = make_instr_desc(128, PT_D, UmmaFmt<T>::value, 0, 1);      // B = V, MN-major
+            mbar_wait(smem_u32(&bars->q_full), 0);
+            int js = 0, jp[2] = {0, 0};
+            const int nk[2] = {nkt_a, nkt_b};
+            uint32_t spins = 0;
+            while (jp[0] < nkt_a || jp[1] < nkt_b) {
+                bool progressed = false;
+                if (js < nkt) {      // S_A(js), S_B(js)
+                    const int st = js % PT_STAGES;
+                    const bool ua = js < nkt_a, ub = js < nkt_b;
+                    const uint32_t spar = (js & 1) ^ 1;
+                    if (mbar_test_wait(smem_u32(&bars->k_full[st]), (js / PT_STAGES) & 1) &&
+                        (!ua || mbar_test_wait(smem_u32(&bars->s_empty[0]), spar)) &&
+                        (!ub || mbar_test_wait(smem_u32(&bars->s_empty[1]), spar))) {
+                        tc_fence_after();
+                        const uint32_t kbase = smem_u32(k_sm + st * PT_KV_BYTES);
+                        for (int x = 0; x < 2; x++) {
+                            if (!(x == 0 ? ua : ub)) continue;
+                            const uint32_t qbase = smem_u32(q_sm + x * PT_Q_BYTES);
+#pragma unroll
+                            for (int ks = 0; ks < 8; ks++) {
+                                const uint64_t a = make_smem_desc(qbase + (ks >> 2) * (PT_Q_BYTES / 2) + (ks & 3) * 32, 16, 1024);
+                                const uint64_t b = make_smem_desc(kbase + (ks >> 2) * (PT_KV_BYTES / 2) + (ks & 3) * 32, 16, 1024);
+                                umma_ss(tmem + x * 64, a, b, IDESC_S, ks > 0);
+                            }
+                            umma_commit(smem_u32(&bars->s_full[x]));
+                        }
+                        umma_commit(smem_u32(&bars->k_empty[st]));
+                        js++;
+                        progressed = true;
+                    }
+                }
+                for (int x = 0; x < 2; x++) {     // PV_X(jp[x])
+                    const int j = jp[x];
+                    if (j >= nk[x] || j >= js) continue;
+                    const int st = j % PT_STAGES;
+                    if (mbar_test_wait(smem_u32(&bars->p_full[x]), j & 1) &&
+                        mbar_test_wait(smem_u32(&bars->v_full[st]), (j / PT_STAGES) & 1)) {
+                        tc_fence_after();
+                        const uint32_t vbase = smem_u32(v_sm + st * PT_KV_BYTES);
+                        const uint32_t pbase = smem_u32(p_sm + x * PT_P_BYTES);
+#pragma unroll
+                        for (int kt = 0; kt < 4; kt++) {       // 16 tokens per UMMA
+                            const uint64_t a = make_smem_desc(pbase + kt * 32, 16, 1024);
+                            const uint64_t b = make_smem_desc(vbase + kt * 2048, PT_KV_BYTES / 2, 1024);
+                            umma_ss(tmem + 128 + x * 128, a, b, IDESC_O, (j > 0 || kt > 0) ? 1u : 0u);
+                        }
+                        umma_commit(smem_u32(&bars->p_empty[x]));
+                        // the V stage is free once every tile that uses it has issued its PV
+                        const int other = 1 - x;
+                        if (j >= nk[other] || jp[other] > j) umma_commit(smem_u32(&bars->v_empty[st]));
+                        jp[x]++;
+                        progressed = true;
+                    }
+                }
+                if (progressed) spins = 0;
+                else if (++spins > (1u << 24)) { printf("sllm: prefill MMA watchdog (block %d,%d,%d js=%d jpA=%d jpB=%d)\n", blockIdx.x, blockIdx.y, blockIdx.z, js, jp[0], jp[1]); __trap(); }
+            }
+        }
+    } else {
+        // =========================================================== softmax warps: group x = 0 (tile A) / 1 (tile B)
+        const int x = (warp - 2) >> 2;
+        const int nk_mine = x == 0 ? nkt_a : nkt_b;
+        const int quad = warp & 3;
+        const int row = quad * 32 + lane;                 // row within the tile = TMEM lane
+        const int qi = q0 + x * PT_BQ + row;              // query index within the sequence
+        const uint32_t tlane = (uint32_t)(quad * 32) << 16;
+        const uint32_t s_addr = tmem + tlane + x * 64;
+        const uint32_t o_addr = tmem + tlane + 128 + x * 128;
+        float m_ref = -INFINITY, l = 0.f;
+        for (int j = 0; j < nk_mine; j++) {
+            mbar_wait(smem_u32(&bars->s_full[x]), j & 1);
+            tc_fence_after();
+            uint32_t r0[32], r1[32];
+            tmem_ld32(s_addr, r0);
+            tmem_ld32(s_addr + 32, r1);
+            tmem_ld_wait();
+            tc_fence_before();
+            mbar_arrive(smem_u32(&bars->s_empty[x]));
+
+            const int c0 = j * PT_BK;
+            const bool need_mask = c0 + PT_BK - 1 > q0 + x * PT_BQ || c0 + PT_BK > len;
+            float mx = -INFINITY;
+#pragma unroll
+            for (int i = 0; i < 32; i++) {
+                float a = __uint_as_float(r0[i]) * p.scale_log2e, b = __uint_as_float(r1[i]) * p.scale_log2e;
+                if (need_mask) {
+                    if (c0 + i > qi || c0 + i >= len) a = -INFINITY;
+                    if (c0 + 32 + i > qi || c0 + 32 + i >= len) b = -INFINITY;
+                }
+                r0[i] = __float_as_uint(a); r1[i] = __float_as_uint(b);
+                mx = fmaxf(mx, fmaxf(a, b));
+            }
+            // wait until PV(j-1) of this tile has finished: P buffer reusable and O stable for a rescale
+            mbar_wait(smem_u32(&bars->p_empty[x]), (j & 1) ^ 1);
+            const float m_new = fmaxf(m_ref, mx);
+            if (m_new > m_ref + PT_RESCALE_THRESHOLD) {          // includes the first tile (m_ref = -inf)
+                if (j > 0) {
+                    const float alpha = fast_exp2_tc(m_ref - m_new);
+                    l *= alpha;
+                    tc_fence_after();
+#pragma unroll
+                    for (int cc = 0; cc < 4; cc++) {
+                        uint32_t t[32];
+                        tmem_ld32(o_addr + cc * 32, t);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int i = 0; i < 32; i++) t[i] = __float_as_uint(__uint_as_float(t[i]) * alpha);
+                        tmem_st32(o_addr + cc * 32, t);
+                    }
+                    tmem_st_wait();
+                    tc_fence_before();
+                }
+                m_ref = m_new;
+            }
+            // p = exp2(s - m_ref) (<= 2^8), row sum in fp32, P row -> shared memory ([128 rows][128 B], SWIZZLE_128B)
+            float ls = 0.f;
+            uint8_t* prow = p_sm + x * PT_P_BYTES + row * 128;
+#pragma unroll
+            for (int c = 0; c < 8; c++) {                         // 8 chunks of 8 tokens
+                uint32_t w[4];
+#pragma unroll
+                for (int e = 0; e < 4; e++) {
+                    const int i = c * 8 + e * 2;                  // token pair (i, i+1) of this 64-token step
+                    const float a = fast_exp2_tc(__uint_as_float(i < 32 ? r0[i] : r1[i - 32]) - m_ref);
+                    const float b = fast_exp2_tc(__uint_as_float(i + 1 < 32 ? r0[i + 1] : r1[i + 1 - 32]) - m_ref);
+                    ls += a + b;
+                    typename Traits<T>::T2 v2 = Traits<T>::from_f2(make_float2(a, b));
+                    w[e] = *reinterpret_cast<uint32_t*>(&v2);
+                }
+                *reinterpret_cast<uint4*>(prow + ((c ^ (row & 7)) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
+            }
+            l += ls;
+            fence_proxy_async();
+            mbar_arrive(smem_u32(&bars->p_full[x]));
+        }
+        if (nk_mine > 0) {
+            // ---- epilogue: O / l -> global (row qi of this head), only rows inside the sequence
+            mbar_wait(smem_u32(&bars->p_empty[x]), (nk_mine & 1) ^ 1);
+            tc_fence_after();
+            const float inv = 1.0f / l;
+            T* orow = reinterpret_cast<T*>(p.o) + ((int64_t)(tok0 + qi) * p.nq + head) * PT_D;
+#pragma unroll
+            for (int cc = 0; cc < 4; cc++) {
+                uint32_t t[32];
+                tmem_ld32(o_addr + cc * 32, t);
+                tmem_ld_wait();
+                if (qi < len) {
+#pragma unroll
+                    for (int v = 0; v < 4; v++) {
+                        uint32_t w[4];
+#pragma unroll
+                        for (int e = 0; e < 4; e++) {
+                            typename Traits<T>::T2 v2 = Traits<T>::from_f2(make_float2(__uint_as_float(t[v * 8 + e * 2]) * inv,
+                                                                                        __uint_as_float(t[v * 8 + e * 2 + 1]) * inv));
+                            w[e] = *reinterpret_cast<uint32_t*>(&v2);
+                        }
+                        *reinterpret_cast<uint4*>(orow + cc * 32 + v * 8) = make_uint4(w[0], w[1], w[2], w[3]);
+                    }
+                }
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc<PT_TMEM_COLS>(tmem);
+}
+
+// ------------------------------------------------------------------ host side
+namespace {
+std::mutex g_pt_mutex;
+struct PtKey { const void* ptr; uint64_t rows; int cols; int dt; bool operator==(const PtKey& o) const { return ptr == o.ptr && rows == o.rows && cols == o.cols && dt == o.dt; } };
+struct PtKeyHash { size_t operator()(const PtKey& k) const { return std::hash<const void*>()(k.ptr) ^ (k.rows * 1315423911u) ^ (size_t)(k.cols * 31 + k.dt); } };
+std::unordered_map<PtKey, CUtensorMap, PtKeyHash> g_pt_maps;
+
+// 2-D map over a packed [rows, cols] 16-bit tensor, boxes of (64 cols x box_rows), SWIZZLE_128B
+bool pt_map(CUtensorMap* out, const void* ptr, uint64_t rows, int cols, int box_rows, sllm_dtype_t dt) {
+    PtKey key{ptr, rows, cols * 1024 + box_rows, (int)dt};
+    {
+        std::lock_guard<std::mutex> lk(g_pt_mutex);
+        auto it = g_pt_maps.find(key);
+        if (it != g_pt_maps.end()) { *out = it->second; return true; }
+    }
+    TensorMapEncodeFn enc = get_tensor_map_encoder();
+    if (!enc) return false;
+    cuuint64_t dims[2] = {(cuuint64_t)cols, rows};
+    cuuint64_t strides[1] = {(cuuint64_t)cols * 2};
+    cuuint32_t box[2] = {64, (cuuint32_t)box_rows}, es[2] = {1, 1};
+    CUresult r = enc(out, dt == SLLM_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr),
+                     dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return false;
+    std::lock_guard<std::mutex> lk(g_pt_mutex);
+    if (g_pt_maps.size() > 4096) g_pt_maps.clear();
+    g_pt_maps[key] = *out;
+    return true;
+}
+}  // namespace
+
+bool tc_prefill_supported(int head_dim, int64_t num_tokens) {
+    return head_dim == PT_D && num_tokens > 0 && num_tokens < (1LL << 31) && get_tensor_map_encoder() != nullptr;
+}
+
+int launch_prefill_tc(const void* q, const void* k, const void* v, void* o, const int32_t* start_locs, const int32_t* seq_lens,
+                      float scale_log2e, int num_seqs, int max_len, int64_t num_tokens, int nq, int nkv, sllm_dtype_t dtype,
+                      cudaStream_t stream) {
+    CUtensorMap qmap, kmap, vmap;
+    SLLM_REQUIRE(pt_map(&qmap, q, (uint64_t)num_tokens, nq * PT_D, PT_BQ, dtype) &&
+                 pt_map(&kmap, k, (uint64_t)num_tokens, nkv * PT_D, PT_BK, dtype) &&
+                 pt_map(&vmap, v, (uint64_t)num_tokens, nkv * PT_D, PT_BK, dtype),
+                 "prefill_attention: cuTensorMapEncodeTiled failed");
+    PtParams p;
+    p.o = o; p.start_locs = start_locs; p.seq_lens = seq_lens; p.scale_log2e = scale_log2e; p.nq = nq; p.nkv = nkv;
+    dim3 grid((max_len + 2 * PT_BQ - 1) / (2 * PT_BQ), nq, num_seqs);
+    if (dtype == SLLM_F16) {
+        static bool c = false;
+        if (!c) { cudaFuncSetAttribute(prefill_attn_tc_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, PT_SMEM_BYTES); c = true; }
+        prefill_attn_tc_kernel<__half><<<grid, PT_THREADS, PT_SMEM_BYTES, stream>>>(qmap, kmap, vmap, p);
+    } else {
+        static bool c = false;
+        if (!c) { cudaFuncSetAttribute(prefill_attn_tc_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, PT_SMEM_BYTES); c = true; }
+        prefill_attn_tc_kernel<__nv_bfloat16><<<grid, PT_THREADS, PT_SMEM_BYTES, stream>>>(qmap, kmap, vmap, p);
+    }
+    return check_launch("prefill_attention(tcgen05)");
+}
+
+}  // namespace sllm
