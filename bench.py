@@ -310,8 +310,8 @@ def run_ours(args):
     if os.path.exists(tpath) and n == 1 and args.model == "llama3-8b" and B == 256 and S == 4096 and not args.layers:
         tj = json.load(open(tpath))
         traffic, traffic_src = tj["dram_bytes_read"] + tj["dram_bytes_write"], tj["source"]
-    gen = os.environ.get("SLLM_PAGED_ATTN_GEN", "")
-    kname = "paged_attn_kernel (gen 1: cp.async + mma.sync)" if gen == "1" else \
+    pa_gen = os.environ.get("SLLM_PAGED_ATTN_GEN", "")
+    kname = "paged_attn_kernel (gen 1: cp.async + mma.sync)" if pa_gen == "1" else \
         "paged_attn_tc_kernel (gen 2: tcgen05 + TMA, persistent)"
 
     # ---- optional: prefill tokens/s (secondary metric of BASELINE.json)

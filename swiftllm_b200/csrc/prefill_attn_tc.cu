@@ -33,14 +33,14 @@ constexpr int PT_THREADS = 320;
 constexpr int PT_Q_BYTES = PT_BQ * PT_D * 2;          // 32 KiB per query tile ([half][128 rows][128 B])
 constexpr int PT_KV_BYTES = PT_BK * PT_D * 2;         // 16 KiB per K (or V) tile ([half][64 rows][128 B])
 constexpr int PT_P_BYTES = PT_BQ * PT_BK * 2;         // 16 KiB per P tile ([128 rows][128 B])
-constexpr int PT_SMEM_BYTES = 2 * PT_Q_BYTES + 2 * PT_STAGES * PT_KV_BYTES + 2 * PT_P_BYTES + 1024;
+constexpr int PT_SMEM_BYTES = 2 * PT_Q_BYTES + 2 * PT_STAGES * PT_KV_BYTES + 4 * PT_P_BYTES + 1024;   // P double buffered per tile
 constexpr int PT_TMEM_COLS = 512;         // S_A 0..63, S_B 64..127, O_A 128..255, O_B 256..383
 constexpr float PT_RESCALE_THRESHOLD = 8.0f;          // log2 units
 
 struct PtBarriers {
     uint64_t q_full;
     uint64_t k_full[PT_STAGES], k_empty[PT_STAGES], v_full[PT_STAGES], v_empty[PT_STAGES];
-    uint64_t s_full[2], s_empty[2], p_full[2], p_empty[2];
+    uint64_t s_full[2], s_empty[2], p_full[2][2], p_empty[2][2];      // P: [tile][buffer]
 };
 
 struct PtParams {
@@ -77,8 +77,8 @@ __global__ void __launch_bounds__(PT_THREADS, 1) prefill_attn_tc_kernel(const __
     uint8_t* q_sm = smem;                                       // [2 tiles][2 halves][128 rows][128 B]
     uint8_t* k_sm = q_sm + 2 * PT_Q_BYTES;                      // [stage][2 halves][64 rows][128 B]
     uint8_t* v_sm = k_sm + PT_STAGES * PT_KV_BYTES;
-    uint8_t* p_sm = v_sm + PT_STAGES * PT_KV_BYTES;             // [2 tiles][128 rows][128 B]
-    uint8_t* misc = p_sm + 2 * PT_P_BYTES;
+    uint8_t* p_sm = v_sm + PT_STAGES * PT_KV_BYTES;             // [2 tiles][2 buffers][128 rows][128 B]
+    uint8_t* misc = p_sm + 4 * PT_P_BYTES;
     PtBarriers* bars = reinterpret_cast<PtBarriers*>(misc);
     uint32_t* tmem_base_s = reinterpret_cast<uint32_t*>(misc + 512);
 
@@ -103,7 +103,7 @@ __global__ void __launch_bounds__(PT_THREADS, 1) prefill_attn_tc_kernel(const __
         }
         for (int i = 0; i < 2; i++) {
             mbar_init(smem_u32(&bars->s_full[i]), 1); mbar_init(smem_u32(&bars->s_empty[i]), 128);
-            mbar_init(smem_u32(&bars->p_full[i]), 128); mbar_init(smem_u32(&bars->p_empty[i]), 1);
+            for (int b = 0; b < 2; b++) { mbar_init(smem_u32(&bars->p_full[i][b]), 128); mbar_init(smem_u32(&bars->p_empty[i][b]), 1); }
         }
         mbar_fence_init();
         tma_prefetch_desc(&qmap); tma_prefetch_desc(&kmap); tma_prefetch_desc(&vmap);
@@ -178,18 +178,19 @@ __global__ void __launch_bounds__(PT_THREADS, 1) prefill_attn_tc_kernel(const __
                     const int j = jp[x];
                     if (j >= nk[x] || j >= js) continue;
                     const int st = j % PT_STAGES;
-                    if (mbar_test_wait(smem_u32(&bars->p_full[x]), j & 1) &&
+                    const int pb = j & 1;
+                    if (mbar_test_wait(smem_u32(&bars->p_full[x][pb]), (j >> 1) & 1) &&
                         mbar_test_wait(smem_u32(&bars->v_full[st]), (j / PT_STAGES) & 1)) {
                         tc_fence_after();
                         const uint32_t vbase = smem_u32(v_sm + st * PT_KV_BYTES);
-                        const uint32_t pbase = smem_u32(p_sm + x * PT_P_BYTES);
+                        const uint32_t pbase = smem_u32(p_sm + (x * 2 + pb) * PT_P_BYTES);
 #pragma unroll
                         for (int kt = 0; kt < 4; kt++) {       // 16 tokens per UMMA
                             const uint64_t a = make_smem_desc(pbase + kt * 32, 16, 1024);
                             const uint64_t b = make_smem_desc(vbase + kt * 2048, PT_KV_BYTES / 2, 1024);
                             umma_ss(tmem + 128 + x * 128, a, b, IDESC_O, (j > 0 || kt > 0) ? 1u : 0u);
                         }
-                        umma_commit(smem_u32(&bars->p_empty[x]));
+                        umma_commit(smem_u32(&bars->p_empty[x][pb]));
                         // the V stage is free once every tile that uses it has issued its PV
                         const int other = 1 - x;
                         if (j >= nk[other] || jp[other] > j) umma_commit(smem_u32(&bars->v_empty[st]));
@@ -224,22 +225,22 @@ __global__ void __launch_bounds__(PT_THREADS, 1) prefill_attn_tc_kernel(const __
 
             const int c0 = j * PT_BK;
             const bool need_mask = c0 + PT_BK - 1 > q0 + x * PT_BQ || c0 + PT_BK > len;
-            float mx = -INFINITY;
+            float mx = -INFINITY;                                  // max of the RAW scores (scale > 0 commutes with max)
 #pragma unroll
             for (int i = 0; i < 32; i++) {
-                float a = __uint_as_float(r0[i]) * p.scale_log2e, b = __uint_as_float(r1[i]) * p.scale_log2e;
+                float a = __uint_as_float(r0[i]), b = __uint_as_float(r1[i]);
                 if (need_mask) {
                     if (c0 + i > qi || c0 + i >= len) a = -INFINITY;
                     if (c0 + 32 + i > qi || c0 + 32 + i >= len) b = -INFINITY;
+                    r0[i] = __float_as_uint(a); r1[i] = __float_as_uint(b);
                 }
-                r0[i] = __float_as_uint(a); r1[i] = __float_as_uint(b);
                 mx = fmaxf(mx, fmaxf(a, b));
             }
-            // wait until PV(j-1) of this tile has finished: P buffer reusable and O stable for a rescale
-            mbar_wait(smem_u32(&bars->p_empty[x]), (j & 1) ^ 1);
-            const float m_new = fmaxf(m_ref, mx);
+            const float m_new = fmaxf(m_ref, mx * p.scale_log2e);
             if (m_new > m_ref + PT_RESCALE_THRESHOLD) {          // includes the first tile (m_ref = -inf)
                 if (j > 0) {
+                    // O must be stable: wait until PV(j-1) of this tile has completed, then rescale this thread's row
+                    mbar_wait(smem_u32(&bars->p_empty[x][(j - 1) & 1]), ((j - 1) >> 1) & 1);
                     const float alpha = fast_exp2_tc(m_ref - m_new);
                     l *= alpha;
                     tc_fence_after();
@@ -257,30 +258,34 @@ __global__ void __launch_bounds__(PT_THREADS, 1) prefill_attn_tc_kernel(const __
                 }
                 m_ref = m_new;
             }
-            // p = exp2(s - m_ref) (<= 2^8), row sum in fp32, P row -> shared memory ([128 rows][128 B], SWIZZLE_128B)
+            // P buffer (j & 1) was last read by PV(j-2)
+            const int pb = j & 1;
+            if (j >= 2) mbar_wait(smem_u32(&bars->p_empty[x][pb]), ((j - 2) >> 1) & 1);
+            // p = exp2(s*c - m_ref) (<= 2^8), row sum in fp32, P row -> shared memory ([128 rows][128 B], SWIZZLE_128B)
             float ls = 0.f;
-            uint8_t* prow = p_sm + x * PT_P_BYTES + row * 128;
+            const float neg_m = -m_ref, c = p.scale_log2e;
+            uint8_t* prow = p_sm + (x * 2 + pb) * PT_P_BYTES + row * 128;
 #pragma unroll
-            for (int c = 0; c < 8; c++) {                         // 8 chunks of 8 tokens
+            for (int ch = 0; ch < 8; ch++) {                       // 8 chunks of 8 tokens
                 uint32_t w[4];
 #pragma unroll
                 for (int e = 0; e < 4; e++) {
-                    const int i = c * 8 + e * 2;                  // token pair (i, i+1) of this 64-token step
-                    const float a = fast_exp2_tc(__uint_as_float(i < 32 ? r0[i] : r1[i - 32]) - m_ref);
-                    const float b = fast_exp2_tc(__uint_as_float(i + 1 < 32 ? r0[i + 1] : r1[i + 1 - 32]) - m_ref);
+                    const int i = ch * 8 + e * 2;                  // token pair (i, i+1) of this 64-token step
+                    const float a = fast_exp2_tc(fmaf(__uint_as_float(i < 32 ? r0[i] : r1[i - 32]), c, neg_m));
+                    const float b = fast_exp2_tc(fmaf(__uint_as_float(i + 1 < 32 ? r0[i + 1] : r1[i + 1 - 32]), c, neg_m));
                     ls += a + b;
                     typename Traits<T>::T2 v2 = Traits<T>::from_f2(make_float2(a, b));
                     w[e] = *reinterpret_cast<uint32_t*>(&v2);
                 }
-                *reinterpret_cast<uint4*>(prow + ((c ^ (row & 7)) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
+                *reinterpret_cast<uint4*>(prow + ((ch ^ (row & 7)) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
             }
             l += ls;
             fence_proxy_async();
-            mbar_arrive(smem_u32(&bars->p_full[x]));
+            mbar_arrive(smem_u32(&bars->p_full[x][pb]));
         }
         if (nk_mine > 0) {
             // ---- epilogue: O / l -> global (row qi of this head), only rows inside the sequence
-            mbar_wait(smem_u32(&bars->p_empty[x]), (nk_mine & 1) ^ 1);
+            mbar_wait(smem_u32(&bars->p_empty[x][(nk_mine - 1) & 1]), ((nk_mine - 1) >> 1) & 1);   // PV(last) done => all done
             tc_fence_after();
             const float inv = 1.0f / l;
             T* orow = reinterpret_cast<T*>(p.o) + ((int64_t)(tok0 + qi) * p.nq + head) * PT_D;
