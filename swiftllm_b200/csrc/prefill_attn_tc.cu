@@ -226,16 +226,17 @@ __global__ void __launch_bounds__(PT_THREADS, 1) prefill_attn_tc_kernel(const __
             const int c0 = j * PT_BK;
             const bool need_mask = c0 + PT_BK - 1 > q0 + x * PT_BQ || c0 + PT_BK > len;
             float mx = -INFINITY;                                  // max of the RAW scores (scale > 0 commutes with max)
+            if (need_mask) {
+                // column c0+i is visible iff c0+i <= qi and c0+i < len  <=>  i <= lim   (branch-free selects)
+                const int lim = min(qi, len - 1) - c0;
 #pragma unroll
-            for (int i = 0; i < 32; i++) {
-                float a = __uint_as_float(r0[i]), b = __uint_as_float(r1[i]);
-                if (need_mask) {
-                    if (c0 + i > qi || c0 + i >= len) a = -INFINITY;
-                    if (c0 + 32 + i > qi || c0 + 32 + i >= len) b = -INFINITY;
-                    r0[i] = __float_as_uint(a); r1[i] = __float_as_uint(b);
+                for (int i = 0; i < 32; i++) {
+                    r0[i] = i <= lim ? r0[i] : 0xff800000u;        // -inf
+                    r1[i] = i + 32 <= lim ? r1[i] : 0xff800000u;
                 }
-                mx = fmaxf(mx, fmaxf(a, b));
             }
+#pragma unroll
+            for (int i = 0; i < 32; i++) mx = fmaxf(mx, fmaxf(__uint_as_float(r0[i]), __uint_as_float(r1[i])));
             const float m_new = fmaxf(m_ref, mx * p.scale_log2e);
             if (m_new > m_ref + PT_RESCALE_THRESHOLD) {          // includes the first tile (m_ref = -inf)
                 if (j > 0) {
