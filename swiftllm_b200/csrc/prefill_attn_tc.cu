@@ -238,27 +238,28 @@ __global__ void __launch_bounds__(PT_THREADS, 1) prefill_attn_tc_kernel(const __
 #pragma unroll
             for (int i = 0; i < 32; i++) mx = fmaxf(mx, fmaxf(__uint_as_float(r0[i]), __uint_as_float(r1[i])));
             const float m_new = fmaxf(m_ref, mx * p.scale_log2e);
-            if (m_new > m_ref + PT_RESCALE_THRESHOLD) {          // includes the first tile (m_ref = -inf)
-                if (j > 0) {
-                    // O must be stable: wait until PV(j-1) of this tile has completed, then rescale this thread's row
-                    mbar_wait(smem_u32(&bars->p_empty[x][(j - 1) & 1]), ((j - 1) >> 1) & 1);
-                    const float alpha = fast_exp2_tc(m_ref - m_new);
-                    l *= alpha;
-                    tc_fence_after();
+            // Lazy rescale.  The decision is per row, but tcgen05.ld/st are warp-collective (.sync.aligned): vote, and
+            // let rows that do not need it take part with alpha = 1.
+            const bool need = m_new > m_ref + PT_RESCALE_THRESHOLD;   // always true on the first tile (m_ref = -inf)
+            if (j > 0 && __any_sync(0xffffffffu, need)) {
+                // O must be stable: wait until PV(j-1) of this tile has completed, then rescale this thread's row
+                mbar_wait(smem_u32(&bars->p_empty[x][(j - 1) & 1]), ((j - 1) >> 1) & 1);
+                const float alpha = need ? fast_exp2_tc(m_ref - m_new) : 1.0f;
+                l *= alpha;
+                tc_fence_after();
 #pragma unroll
-                    for (int cc = 0; cc < 4; cc++) {
-                        uint32_t t[32];
-                        tmem_ld32(o_addr + cc * 32, t);
-                        tmem_ld_wait();
+                for (int cc = 0; cc < 4; cc++) {
+                    uint32_t t[32];
+                    tmem_ld32(o_addr + cc * 32, t);
+                    tmem_ld_wait();
 #pragma unroll
-                        for (int i = 0; i < 32; i++) t[i] = __float_as_uint(__uint_as_float(t[i]) * alpha);
-                        tmem_st32(o_addr + cc * 32, t);
-                    }
-                    tmem_st_wait();
-                    tc_fence_before();
+                    for (int i = 0; i < 32; i++) t[i] = __float_as_uint(__uint_as_float(t[i]) * alpha);
+                    tmem_st32(o_addr + cc * 32, t);
                 }
-                m_ref = m_new;
+                tmem_st_wait();
+                tc_fence_before();
             }
+            if (need) m_ref = m_new;
             // P buffer (j & 1) was last read by PV(j-2)
             const int pb = j & 1;
             if (j >= 2) mbar_wait(smem_u32(&bars->p_empty[x][pb]), ((j - 2) >> 1) & 1);

@@ -426,6 +426,31 @@ def test_prefill_attention_vs_exact_oracle(dtype, geom, prefill_gen):
     assert (o[sum(lens):] == 0).all()
 
 
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_prefill_attention_growing_scores_force_rescales(dtype, prefill_gen):
+    """Adversarial for the lazy-rescale path of the tcgen05 kernel: key magnitudes grow along the sequence and differ
+    per row parity, so the running max of SOME rows of a warp jumps by more than 2^8 at several kv steps while their
+    neighbours' does not (a per-thread decision around warp-collective TMEM loads/stores must not diverge)."""
+    nq, nkv, D = 4, 2, 128
+    lens = [700, 333]
+    starts = [0, 700]
+    Tn = sum(lens)
+    g = torch.Generator().manual_seed(77)
+    q = torch.randn(Tn, nq, D, generator=g)
+    k = torch.randn(Tn, nkv, D, generator=g)
+    v = torch.randn(Tn, nkv, D, generator=g)
+    pos = torch.cat([torch.arange(n) for n in lens]).float()
+    k = k * (1.0 + pos / 40.0)[:, None, None]                 # scores grow with the key position
+    q[::2] *= 6.0                                             # even rows: large logits (frequent rescales); odd rows: small
+    q[1::2] *= 0.05
+    q, k, v = q.to(dtype), k.to(dtype), v.to(dtype)
+    o = _prefill_run(q, k, v, starts, lens, D ** -0.5)
+    o64 = K.prefill_attention_exact(q, k, v, starts, lens, D ** -0.5)
+    tol = 2e-3 if dtype == torch.float16 else 1e-2
+    assert torch.isfinite(o.float()).all()
+    assert (o.double() - o64).abs().max() <= tol * o64.abs().max()
+
+
 def test_prefill_attention_long_sequence_property(prefill_gen):
     """4096-token prompt (the prefill tok/s shape): the last row of causal attention equals decode attention over
     the same keys, so prefill's final row must match the paged-decode kernel's output for the same data."""
