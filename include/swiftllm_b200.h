@@ -47,10 +47,11 @@ int sllm_fused_add_rmsnorm_inplace(void* x, void* residual, const void* weight, 
 
 /* ---- Rotary embedding: swiftllm/worker/kernels/rotary_emb.py:44-58 (rotary_embedding_inplace)
  * q [T, nq, D], k [T, nkv, D] in place; cos/sin [T, D/2] (infer_state.position_cos/sin).  NeoX half-split.
- * D % 16 == 0. */
+ * D % 16 == 0.  *_row_stride: elements between consecutive token rows (nq*D / nkv*D when contiguous, as in the
+ * reference; larger when q/k/v are column slices of one fused QKV GEMM output); heads stay contiguous within a token. */
 int sllm_rotary_embedding_inplace(void* q, void* k, const void* cos, const void* sin, int64_t num_tokens,
-                                  int num_q_heads, int num_kv_heads, int head_dim, sllm_dtype_t dtype,
-                                  sllm_stream_t stream);
+                                  int num_q_heads, int num_kv_heads, int head_dim, int64_t q_row_stride,
+                                  int64_t k_row_stride, sllm_dtype_t dtype, sllm_stream_t stream);
 
 /* ---- SwiGLU gate: swiftllm/worker/kernels/silu_and_mul.py:25-34 (silu_and_mul_inplace)
  * x [T, 2*ffn_inter_dim] = [up | gate]; x[:, :F] <- up * silu(gate).  F % 8 == 0. */
@@ -66,7 +67,7 @@ int sllm_store_kvcache(const void* k, const void* v, void* k_cache, void* v_cach
                        const int32_t* prefill_seq_lens, const int32_t* decoding_seq_lens, int num_prefill_seqs,
                        int num_decoding_seqs, int64_t num_prefill_tokens, int max_prefill_len, int cur_layer,
                        int num_layers, int num_kv_heads, int block_size, int head_dim, int max_blocks_per_seq,
-                       sllm_dtype_t dtype, sllm_stream_t stream);
+                       int64_t k_row_stride, int64_t v_row_stride, sllm_dtype_t dtype, sllm_stream_t stream);
 
 /* ---- Paged (decode) attention: swiftllm/worker/kernels/paged_attn.py:152-222 (paged_attention)
  * q [Bd, nq, D]; o [Bd, nq*D]; seq_ids = infer_state.seq_ids[num_prefill_seqs:]; seq_lens = decoding_seq_lens.
@@ -81,7 +82,7 @@ int sllm_paged_attention(const void* q, const void* k_cache, const void* v_cache
                          int64_t workspace_bytes, float softmax_scale, int num_decoding_seqs, int max_seq_len,
                          int seq_block_size, int cur_layer, int num_layers, int num_q_heads, int num_kv_heads,
                          int block_size, int head_dim, int max_blocks_per_seq, int64_t num_blocks,
-                         sllm_dtype_t dtype, sllm_stream_t stream);
+                         int64_t q_row_stride, sllm_dtype_t dtype, sllm_stream_t stream);
 
 /* ---- Prefill attention: swiftllm/worker/kernels/prefill_attn.py:102-139 (prefill_attention) and the
  * flash_attn_varlen_func call it stands for (swiftllm/worker/layers/transformer_layer.py:86-96).
@@ -89,7 +90,8 @@ int sllm_paged_attention(const void* q, const void* k_cache, const void* v_cache
 int sllm_prefill_attention(const void* q, const void* k, const void* v, void* o, const int32_t* prefill_seq_start_locs,
                            const int32_t* prefill_seq_lens, float softmax_scale, int num_prefill_seqs,
                            int max_prefill_len, int64_t num_prefill_tokens, int num_q_heads, int num_kv_heads,
-                           int head_dim, sllm_dtype_t dtype, sllm_stream_t stream);
+                           int head_dim, int64_t q_row_stride, int64_t k_row_stride, int64_t v_row_stride,
+                           sllm_dtype_t dtype, sllm_stream_t stream);
 
 /* ---- Block-table maintenance: swiftllm/worker/kernels/block_mgmt.py:26-46, :66-80, :106-127
  * block_table int32 [max_seqs, max_blocks_per_seq]; num_seq_allocated_blocks int32 [max_seqs];

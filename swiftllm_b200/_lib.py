@@ -24,12 +24,12 @@ SIGNATURES = {
     "sllm_device_check": (_I, [_I]),
     "sllm_rmsnorm_inplace": (_I, [_P, _P, _F, _L, _I, _I, _P]),
     "sllm_fused_add_rmsnorm_inplace": (_I, [_P, _P, _P, _F, _L, _I, _I, _P]),
-    "sllm_rotary_embedding_inplace": (_I, [_P, _P, _P, _P, _L, _I, _I, _I, _I, _P]),
+    "sllm_rotary_embedding_inplace": (_I, [_P, _P, _P, _P, _L, _I, _I, _I, _L, _L, _I, _P]),
     "sllm_silu_and_mul_inplace": (_I, [_P, _L, _L, _I, _P]),
-    "sllm_store_kvcache": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _L, _I, _I, _I, _I, _I, _I, _I, _I, _P]),
+    "sllm_store_kvcache": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _L, _I, _I, _I, _I, _I, _I, _I, _L, _L, _I, _P]),
     "sllm_paged_attention_workspace_bytes": (_L, [_I, _I, _I, _I, _I, _I]),
-    "sllm_paged_attention": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _L, _F, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _L, _I, _P]),
-    "sllm_prefill_attention": (_I, [_P, _P, _P, _P, _P, _P, _F, _I, _I, _L, _I, _I, _I, _I, _P]),
+    "sllm_paged_attention": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _L, _F, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _L, _L, _I, _P]),
+    "sllm_prefill_attention": (_I, [_P, _P, _P, _P, _P, _P, _F, _I, _I, _L, _I, _I, _I, _L, _L, _L, _I, _P]),
     "sllm_set_block_table_and_num_seq_alloc_blocks": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _P]),
     "sllm_unset_block_table_and_num_seq_alloc_blocks": (_I, [_P, _P, _P, _P, _I, _I, _P]),
     "sllm_gather_allocated_blocks_and_unset": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _P]),
@@ -91,6 +91,14 @@ def stream() -> int:
 
 def ptr(t) -> int:
     return 0 if t is None else t.data_ptr()
+
+
+def row_stride(t: torch.Tensor) -> int:
+    """Elements between consecutive token rows of a [T, heads, D] tensor whose heads/D are contiguous within a token
+    (a contiguous tensor, as in the reference, or a column slice of a fused QKV GEMM output)."""
+    assert t.dim() == 3 and t.stride(2) == 1 and t.stride(1) == t.shape[2], \
+        "expected [tokens, heads, head_dim] with heads and head_dim contiguous within a token"
+    return t.stride(0) if t.shape[0] > 1 else max(t.stride(0), t.shape[1] * t.shape[2])
 
 
 _checked_devices = set()

@@ -81,7 +81,7 @@ static int launch_rmsnorm(void* x, void* residual, const void* weight, float eps
 template <typename T>
 __global__ void __launch_bounds__(256) rotary_kernel(T* __restrict__ q, T* __restrict__ k, const T* __restrict__ cosb,
                                                      const T* __restrict__ sinb, int64_t total, int nq, int nkv,
-                                                     int head_dim) {
+                                                     int head_dim, int64_t q_stride, int64_t k_stride) {
     const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= total) return;
     const int chunks = head_dim >> 4;             // 8-wide chunks in half a head
@@ -89,7 +89,7 @@ __global__ void __launch_bounds__(256) rotary_kernel(T* __restrict__ q, T* __res
     const int c = (int)(idx % chunks);
     const int hh = (int)((idx / chunks) % heads);
     const int64_t t = idx / ((int64_t)chunks * heads);
-    T* base = hh < nq ? q + (t * nq + hh) * head_dim : k + (t * nkv + (hh - nq)) * head_dim;
+    T* base = hh < nq ? q + t * q_stride + hh * head_dim : k + t * k_stride + (hh - nq) * head_dim;
     const int half = head_dim >> 1;
     Vec8<T> x0 = ld_vec8(base + 8 * c), x1 = ld_vec8(base + half + 8 * c);
     Vec8<T> cv = ld_vec8(cosb + t * half + 8 * c), sv = ld_vec8(sinb + t * half + 8 * c);
@@ -149,9 +149,12 @@ int sllm_fused_add_rmsnorm_inplace(void* x, void* residual, const void* weight, 
 }
 
 int sllm_rotary_embedding_inplace(void* q, void* k, const void* cosb, const void* sinb, int64_t num_tokens,
-                                  int num_q_heads, int num_kv_heads, int head_dim, sllm_dtype_t dtype,
-                                  sllm_stream_t stream) {
+                                  int num_q_heads, int num_kv_heads, int head_dim, int64_t q_row_stride,
+                                  int64_t k_row_stride, sllm_dtype_t dtype, sllm_stream_t stream) {
     SLLM_REQUIRE(head_dim > 0 && head_dim % 16 == 0, "rotary: head_dim (%d) must be a multiple of 16", head_dim);
+    SLLM_REQUIRE(q_row_stride >= (int64_t)num_q_heads * head_dim && k_row_stride >= (int64_t)num_kv_heads * head_dim &&
+                 q_row_stride % 8 == 0 && k_row_stride % 8 == 0, "rotary: bad row strides (%lld, %lld)",
+                 (long long)q_row_stride, (long long)k_row_stride);
     SLLM_REQUIRE(num_q_heads > 0 && num_kv_heads > 0 && num_tokens >= 0, "rotary: bad shape");
     if (num_tokens == 0) return 0;
     SLLM_REQUIRE(q && k && cosb && sinb, "rotary: null pointer");
@@ -159,7 +162,8 @@ int sllm_rotary_embedding_inplace(void* q, void* k, const void* cosb, const void
     const int threads = 256;
     const unsigned blocks = (unsigned)((total + threads - 1) / threads);
     SLLM_DISPATCH_DTYPE(dtype, (rotary_kernel<T><<<blocks, threads, 0, (cudaStream_t)stream>>>(
-                                   (T*)q, (T*)k, (const T*)cosb, (const T*)sinb, total, num_q_heads, num_kv_heads, head_dim)));
+                                   (T*)q, (T*)k, (const T*)cosb, (const T*)sinb, total, num_q_heads, num_kv_heads, head_dim,
+                                   q_row_stride, k_row_stride)));
     return check_launch("rotary_embedding");
 }
 

@@ -15,23 +15,23 @@ __global__ void __launch_bounds__(256) store_kv_prefill_kernel(
     const T* __restrict__ k, const T* __restrict__ v, T* __restrict__ k_cache, T* __restrict__ v_cache,
     const int32_t* __restrict__ block_table, const int32_t* __restrict__ seq_ids,
     const int32_t* __restrict__ start_locs, const int32_t* __restrict__ seq_lens, int cur_layer, int num_layers,
-    int nkv, int bs, int D, int max_blocks_per_seq) {
+    int nkv, int bs, int D, int max_blocks_per_seq, int64_t k_stride, int64_t v_stride) {
     const int b = blockIdx.y, pb = blockIdx.x;
     const int len = seq_lens[b];
     const int tok0 = pb * bs;
     if (tok0 >= len) return;
     const int ntok = min(bs, len - tok0);
-    const int64_t src0 = (int64_t)(start_locs[b] + tok0) * nkv * D;
+    const int64_t row0 = start_locs[b] + tok0;
     const int64_t blk = block_table[(int64_t)seq_ids[b] * max_blocks_per_seq + pb];
     const int64_t dst0 = (blk * num_layers + cur_layer) * (int64_t)nkv * bs * D;
     const int cpr = D >> 3;                     // 16-byte chunks per D-row
     const int items = ntok * nkv * cpr;
     for (int i = threadIdx.x; i < items; i += blockDim.x) {
         const int c = i % cpr, h = (i / cpr) % nkv, t = i / (cpr * nkv);
-        const int64_t s = src0 + ((int64_t)t * nkv + h) * D + 8 * c;
+        const int64_t so = (int64_t)h * D + 8 * c;
         const int64_t d = dst0 + ((int64_t)h * bs + t) * D + 8 * c;
-        st_vec8(k_cache + d, ld_vec8_stream(k + s));
-        st_vec8(v_cache + d, ld_vec8_stream(v + s));
+        st_vec8(k_cache + d, ld_vec8_stream(k + (row0 + t) * k_stride + so));
+        st_vec8(v_cache + d, ld_vec8_stream(v + (row0 + t) * v_stride + so));
     }
 }
 
@@ -42,20 +42,19 @@ __global__ void __launch_bounds__(128) store_kv_decode_kernel(
     const T* __restrict__ k, const T* __restrict__ v, T* __restrict__ k_cache, T* __restrict__ v_cache,
     const int32_t* __restrict__ block_table, const int32_t* __restrict__ seq_ids,
     const int32_t* __restrict__ seq_lens, int cur_layer, int num_layers, int nkv, int bs, int D,
-    int max_blocks_per_seq) {
+    int max_blocks_per_seq, int64_t k_stride, int64_t v_stride) {
     const int b = blockIdx.x;
     const int pos = seq_lens[b] - 1;
     const int64_t blk = block_table[(int64_t)seq_ids[b] * max_blocks_per_seq + pos / bs];
     const int off = pos % bs;
-    const int64_t src0 = (int64_t)b * nkv * D;
     const int64_t dst0 = (blk * num_layers + cur_layer) * (int64_t)nkv * bs * D + (int64_t)off * D;
     const int cpr = D >> 3;
     for (int i = threadIdx.x; i < nkv * cpr; i += blockDim.x) {
         const int c = i % cpr, h = i / cpr;
-        const int64_t s = src0 + (int64_t)h * D + 8 * c;
+        const int64_t so = (int64_t)h * D + 8 * c;
         const int64_t d = dst0 + (int64_t)h * bs * D + 8 * c;
-        st_vec8(k_cache + d, ld_vec8(k + s));
-        st_vec8(v_cache + d, ld_vec8(v + s));
+        st_vec8(k_cache + d, ld_vec8(k + (int64_t)b * k_stride + so));
+        st_vec8(v_cache + d, ld_vec8(v + (int64_t)b * v_stride + so));
     }
 }
 
@@ -224,8 +223,11 @@ int sllm_store_kvcache(const void* k, const void* v, void* k_cache, void* v_cach
                        const int32_t* seq_ids, const int32_t* prefill_seq_start_locs, const int32_t* prefill_seq_lens,
                        const int32_t* decoding_seq_lens, int num_prefill_seqs, int num_decoding_seqs,
                        int64_t num_prefill_tokens, int max_prefill_len, int cur_layer, int num_layers, int nkv,
-                       int block_size, int head_dim, int max_blocks_per_seq, sllm_dtype_t dtype, sllm_stream_t stream_) {
+                       int block_size, int head_dim, int max_blocks_per_seq, int64_t k_row_stride, int64_t v_row_stride,
+                       sllm_dtype_t dtype, sllm_stream_t stream_) {
     SLLM_REQUIRE(head_dim > 0 && head_dim % 8 == 0, "store_kvcache: head_dim (%d) must be a multiple of 8", head_dim);
+    SLLM_REQUIRE(k_row_stride >= (int64_t)nkv * head_dim && v_row_stride >= (int64_t)nkv * head_dim && k_row_stride % 8 == 0 &&
+                 v_row_stride % 8 == 0, "store_kvcache: bad row strides (%lld, %lld)", (long long)k_row_stride, (long long)v_row_stride);
     SLLM_REQUIRE(block_size > 0 && nkv > 0 && num_layers > 0 && cur_layer >= 0 && cur_layer < num_layers,
                  "store_kvcache: bad cache geometry (layer %d of %d)", cur_layer, num_layers);
     SLLM_REQUIRE(num_prefill_seqs >= 0 && num_decoding_seqs >= 0, "store_kvcache: negative batch");
@@ -238,19 +240,19 @@ int sllm_store_kvcache(const void* k, const void* v, void* k_cache, void* v_cach
         SLLM_DISPATCH_DTYPE(dtype, (store_kv_prefill_kernel<T><<<grid, 256, 0, stream>>>(
                                        (const T*)k, (const T*)v, (T*)k_cache, (T*)v_cache, block_table, seq_ids,
                                        prefill_seq_start_locs, prefill_seq_lens, cur_layer, num_layers, nkv, block_size,
-                                       head_dim, max_blocks_per_seq)));
+                                       head_dim, max_blocks_per_seq, k_row_stride, v_row_stride)));
         int e = check_launch("store_kvcache(prefill)");
         if (e) return e;
     }
     if (num_decoding_seqs > 0) {
         SLLM_REQUIRE(decoding_seq_lens, "store_kvcache: null decoding_seq_lens");
         const size_t elem = 2;
-        const char* kd = (const char*)k + (size_t)num_prefill_tokens * nkv * head_dim * elem;
-        const char* vd = (const char*)v + (size_t)num_prefill_tokens * nkv * head_dim * elem;
+        const char* kd = (const char*)k + (size_t)num_prefill_tokens * (size_t)k_row_stride * elem;
+        const char* vd = (const char*)v + (size_t)num_prefill_tokens * (size_t)v_row_stride * elem;
         SLLM_DISPATCH_DTYPE(dtype, (store_kv_decode_kernel<T><<<num_decoding_seqs, 128, 0, stream>>>(
                                        (const T*)kd, (const T*)vd, (T*)k_cache, (T*)v_cache, block_table,
                                        seq_ids + num_prefill_seqs, decoding_seq_lens, cur_layer, num_layers, nkv,
-                                       block_size, head_dim, max_blocks_per_seq)));
+                                       block_size, head_dim, max_blocks_per_seq, k_row_stride, v_row_stride)));
         return check_launch("store_kvcache(decode)");
     }
     return 0;

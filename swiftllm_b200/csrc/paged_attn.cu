@@ -28,6 +28,7 @@ struct PagedAttnParams {
     void* o; float* part_o; float* part_lse;
     float scale_log2e;
     int split_tokens, num_splits, cur_layer, num_layers, nq, nkv, block_size, max_blocks_per_seq;
+    int64_t q_stride;                 // elements between consecutive q rows (sequences)
 };
 
 template <typename T, int D>
@@ -85,7 +86,7 @@ __global__ void __launch_bounds__(PA_THREADS, 2) paged_attn_kernel(const PagedAt
     // ---- Q fragments (A operand, 16 x D, rows >= g are zero)
     uint32_t qa[D / 16][4];
     {
-        const T* qb = reinterpret_cast<const T*>(p.q) + ((int64_t)seq * p.nq + (int64_t)kvh * g) * D;
+        const T* qb = reinterpret_cast<const T*>(p.q) + (int64_t)seq * p.q_stride + (int64_t)kvh * g * D;
         const int r0 = lane >> 2, r1 = r0 + 8, c0 = (lane & 3) * 2;
 #pragma unroll
         for (int ks = 0; ks < D / 16; ks++) {
@@ -276,7 +277,7 @@ bool tc_paged_supported(int head_dim, int block_size, int nq, int nkv, int64_t n
 int launch_paged_tc(const void* q, const void* k_cache, const void* v_cache, const int32_t* block_table, const int32_t* seq_ids,
                     const int32_t* seq_lens, void* o, float* part_o, float* part_lse, float scale_log2e, int num_seqs,
                     int split_tokens, int num_splits, int cur_layer, int num_layers, int nq, int nkv, int max_blocks_per_seq,
-                    int64_t num_blocks, sllm_dtype_t dtype, int num_sms, cudaStream_t stream);
+                    int64_t num_blocks, int64_t q_row_stride, sllm_dtype_t dtype, int num_sms, cudaStream_t stream);
 
 // SLLM_PAGED_ATTN_GEN=1 forces the cp.async/mma.sync kernel (A/B measurements, debugging); default: tcgen05/TMA
 // whenever the shape is covered (head_dim 128, block_size 16).
@@ -326,8 +327,8 @@ int sllm_paged_attention(const void* q, const void* k_cache, const void* v_cache
                          const int32_t* seq_ids, const int32_t* seq_lens, void* o, void* workspace,
                          int64_t workspace_bytes, float softmax_scale, int num_decoding_seqs, int max_seq_len,
                          int seq_block_size, int cur_layer, int num_layers, int nq, int nkv, int block_size,
-                         int head_dim, int max_blocks_per_seq, int64_t num_blocks, sllm_dtype_t dtype,
-                         sllm_stream_t stream) {
+                         int head_dim, int max_blocks_per_seq, int64_t num_blocks, int64_t q_row_stride,
+                         sllm_dtype_t dtype, sllm_stream_t stream) {
     SLLM_REQUIRE(num_decoding_seqs >= 0, "paged_attention: negative batch");
     if (num_decoding_seqs == 0) return 0;
     SLLM_REQUIRE(q && k_cache && v_cache && block_table && seq_ids && seq_lens && o, "paged_attention: null pointer");
@@ -336,6 +337,7 @@ int sllm_paged_attention(const void* q, const void* k_cache, const void* v_cache
     SLLM_REQUIRE(block_size > 0 && max_seq_len > 0 && cur_layer >= 0 && cur_layer < num_layers, "paged_attention: bad geometry");
     SLLM_REQUIRE(seq_block_size >= 0 && seq_block_size % block_size == 0,
                  "paged_attention: seq_block_size (%d) must be a multiple of block_size (%d)", seq_block_size, block_size);
+    SLLM_REQUIRE(q_row_stride >= (int64_t)nq * head_dim && q_row_stride % 8 == 0, "paged_attention: bad q row stride %lld", (long long)q_row_stride);
     SLLM_REQUIRE(seq_block_size <= PA_MAX_SPLIT_TOKENS, "paged_attention: seq_block_size %d > %d", seq_block_size, PA_MAX_SPLIT_TOKENS);
     PagedAttnParams p;
     p.q = q; p.k_cache = k_cache; p.v_cache = v_cache; p.block_table = block_table; p.seq_ids = seq_ids; p.seq_lens = seq_lens;
@@ -344,7 +346,7 @@ int sllm_paged_attention(const void* q, const void* k_cache, const void* v_cache
     p.split_tokens = choose_split_tokens(num_decoding_seqs, nkv, max_seq_len, seq_block_size);
     p.num_splits = (max_seq_len + p.split_tokens - 1) / p.split_tokens;
     p.cur_layer = cur_layer; p.num_layers = num_layers; p.nq = nq; p.nkv = nkv; p.block_size = block_size;
-    p.max_blocks_per_seq = max_blocks_per_seq;
+    p.max_blocks_per_seq = max_blocks_per_seq; p.q_stride = q_row_stride;
     p.part_o = nullptr; p.part_lse = nullptr;
     if (p.num_splits > 1) {
         const int64_t need = (int64_t)num_decoding_seqs * nq * p.num_splits * (head_dim + 1) * (int64_t)sizeof(float);
@@ -358,7 +360,7 @@ int sllm_paged_attention(const void* q, const void* k_cache, const void* v_cache
         dtype <= SLLM_BF16) {
         int e = launch_paged_tc(q, k_cache, v_cache, block_table, seq_ids, seq_lens, o, p.part_o, p.part_lse, p.scale_log2e,
                                 num_decoding_seqs, p.split_tokens, p.num_splits, cur_layer, num_layers, nq, nkv,
-                                max_blocks_per_seq, num_blocks, dtype, num_sms(), st);
+                                max_blocks_per_seq, num_blocks, q_row_stride, dtype, num_sms(), st);
         if (e) return e;
         if (p.num_splits > 1) {
             dim3 g2(nq, num_decoding_seqs);

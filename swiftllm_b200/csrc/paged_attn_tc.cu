@@ -102,15 +102,15 @@ __device__ __forceinline__ void producer_loop(const TcParams& p, const CUtensorM
     for (int idx = blockIdx.x; idx < p.num_items; idx += gridDim.x) {
         Item it;
         if (!get_item(p, idx, it)) continue;
-        if (IS_K) {       // Q of this item: rows [seq*nq + kvh*g, +16) x 128 d as two 64-wide boxes
+        if (IS_K) {       // Q of this item: heads [kvh*g, +16) of sequence seq, 128 d as two 64-wide boxes
             const int qb = n & 1;
             if (lane == 0) {
                 mbar_wait(smem_u32(&bars->q_empty[qb]), ((n >> 1) & 1) ^ 1);
                 const uint32_t qbar = smem_u32(&bars->q_full[qb]);
                 mbar_arrive_expect_tx(qbar, TC_Q_BYTES);
-                const int row = it.seq * p.nq + it.kvh * g;
-                tma_load_2d(smem_u32(q_sm + qb * TC_Q_BYTES), qmap, qbar, 0, row);
-                tma_load_2d(smem_u32(q_sm + qb * TC_Q_BYTES + 2048), qmap, qbar, 64, row);
+                // q viewed as (128 d | nq heads | Bd sequences): heads past nq are zero-filled by the TMA unit
+                tma_load_3d(smem_u32(q_sm + qb * TC_Q_BYTES), qmap, qbar, 0, it.kvh * g, it.seq);
+                tma_load_3d(smem_u32(q_sm + qb * TC_Q_BYTES + 2048), qmap, qbar, 64, it.kvh * g, it.seq);
             }
         }
         const int first_page = it.split_start / TC_BS;
@@ -374,11 +374,13 @@ namespace sllm {
 namespace {
 
 struct MapKey {
-    const void* ptr; uint64_t rows; int kind;
-    bool operator==(const MapKey& o) const { return ptr == o.ptr && rows == o.rows && kind == o.kind; }
+    const void* ptr; uint64_t rows; int kind; uint64_t aux;
+    bool operator==(const MapKey& o) const { return ptr == o.ptr && rows == o.rows && kind == o.kind && aux == o.aux; }
 };
 struct MapKeyHash {
-    size_t operator()(const MapKey& k) const { return std::hash<const void*>()(k.ptr) ^ (std::hash<uint64_t>()(k.rows) * 1315423911u) ^ (size_t)k.kind; }
+    size_t operator()(const MapKey& k) const {
+        return std::hash<const void*>()(k.ptr) ^ (std::hash<uint64_t>()(k.rows) * 1315423911u) ^ (size_t)k.kind ^ (std::hash<uint64_t>()(k.aux) << 1);
+    }
 };
 std::mutex g_map_mutex;
 std::unordered_map<MapKey, CUtensorMap, MapKeyHash> g_maps;
@@ -386,8 +388,9 @@ int g_kv_4d_ok = -1;            // -1 unknown, 0 the driver rejected the permute
 
 CUtensorMapDataType map_dtype(sllm_dtype_t dt) { return dt == SLLM_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16; }
 
-// kind 0: 2-D [rows, 128] map with (64 x 16) boxes; kind 1: 4-D page map (64 d | 8 tok | 2 halves | rows/8), box (64,8,2,2)
-bool encode_map(CUtensorMap* out, const void* ptr, uint64_t rows, int kind, sllm_dtype_t dt) {
+// kind 0: 2-D [rows, 128] map with (64 x 16) boxes; kind 1: 4-D page map (64 d | 8 tok | 2 halves | rows/8), box (64,8,2,2);
+// kind 2: q as (128 d | nq heads | rows sequences) with sequence stride aux>>16 elements and nq = aux & 0xffff, box (64,16,1)
+bool encode_map(CUtensorMap* out, const void* ptr, uint64_t rows, int kind, sllm_dtype_t dt, uint64_t aux) {
     TensorMapEncodeFn enc = get_tensor_map_encoder();
     if (!enc) return false;
     CUresult r;
@@ -396,6 +399,12 @@ bool encode_map(CUtensorMap* out, const void* ptr, uint64_t rows, int kind, sllm
         cuuint64_t strides[1] = {256};
         cuuint32_t box[2] = {64, 16}, es[2] = {1, 1};
         r = enc(out, map_dtype(dt), 2, const_cast<void*>(ptr), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    } else if (kind == 2) {
+        cuuint64_t dims[3] = {128, aux & 0xffff, rows};
+        cuuint64_t strides[2] = {256, (aux >> 16) * 2};
+        cuuint32_t box[3] = {64, 16, 1}, es[3] = {1, 1, 1};
+        r = enc(out, map_dtype(dt), 3, const_cast<void*>(ptr), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
                 CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     } else {
         cuuint64_t dims[4] = {64, 8, 2, rows / 8};
@@ -407,14 +416,14 @@ bool encode_map(CUtensorMap* out, const void* ptr, uint64_t rows, int kind, sllm
     return r == CUDA_SUCCESS;
 }
 
-bool get_map(CUtensorMap* out, const void* ptr, uint64_t rows, int kind, sllm_dtype_t dt, bool cache) {
-    MapKey key{ptr, rows, kind * 2 + (int)dt};
+bool get_map(CUtensorMap* out, const void* ptr, uint64_t rows, int kind, sllm_dtype_t dt, bool cache, uint64_t aux = 0) {
+    MapKey key{ptr, rows, kind * 2 + (int)dt, aux};
     if (cache) {
         std::lock_guard<std::mutex> lk(g_map_mutex);
         auto it = g_maps.find(key);
         if (it != g_maps.end()) { *out = it->second; return true; }
     }
-    if (!encode_map(out, ptr, rows, kind, dt)) return false;
+    if (!encode_map(out, ptr, rows, kind, dt, aux)) return false;
     if (cache) {
         std::lock_guard<std::mutex> lk(g_map_mutex);
         if (g_maps.size() > 4096) g_maps.clear();
@@ -437,7 +446,7 @@ bool tc_paged_supported(int head_dim, int block_size, int nq, int nkv, int64_t n
 int launch_paged_tc(const void* q, const void* k_cache, const void* v_cache, const int32_t* block_table, const int32_t* seq_ids,
                     const int32_t* seq_lens, void* o, float* part_o, float* part_lse, float scale_log2e, int num_seqs,
                     int split_tokens, int num_splits, int cur_layer, int num_layers, int nq, int nkv, int max_blocks_per_seq,
-                    int64_t num_blocks, sllm_dtype_t dtype, int num_sms, cudaStream_t stream) {
+                    int64_t num_blocks, int64_t q_row_stride, sllm_dtype_t dtype, int num_sms, cudaStream_t stream) {
     const uint64_t rows = (uint64_t)num_blocks * num_layers * nkv * TC_BS;
     CUtensorMap kmap, vmap, qmap;
     if (g_kv_4d_ok != 0) {
@@ -448,7 +457,8 @@ int launch_paged_tc(const void* q, const void* k_cache, const void* v_cache, con
         SLLM_REQUIRE(get_map(&kmap, k_cache, rows, 0, dtype, true) && get_map(&vmap, v_cache, rows, 0, dtype, true),
                      "paged_attention: cuTensorMapEncodeTiled failed for the KV cache");
     }
-    SLLM_REQUIRE(get_map(&qmap, q, (uint64_t)num_seqs * nq, 0, dtype, true), "paged_attention: cuTensorMapEncodeTiled failed for q");
+    SLLM_REQUIRE(get_map(&qmap, q, (uint64_t)num_seqs, 2, dtype, true, ((uint64_t)q_row_stride << 16) | (uint64_t)nq),
+                 "paged_attention: cuTensorMapEncodeTiled failed for q");
 
     TcParams p;
     p.block_table = block_table; p.seq_ids = seq_ids; p.seq_lens = seq_lens; p.o = o; p.part_o = part_o; p.part_lse = part_lse;

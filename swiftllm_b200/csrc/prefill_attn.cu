@@ -20,7 +20,8 @@ constexpr int PF_THREADS = 256;
 template <typename T, int D>
 __global__ void __launch_bounds__(PF_THREADS, 1) prefill_attn_kernel(
     const T* __restrict__ q, const T* __restrict__ k, const T* __restrict__ v, T* __restrict__ o,
-    const int32_t* __restrict__ start_locs, const int32_t* __restrict__ seq_lens, float scale_log2e, int nq, int nkv) {
+    const int32_t* __restrict__ start_locs, const int32_t* __restrict__ seq_lens, float scale_log2e, int nq, int nkv,
+    int64_t qs, int64_t ks, int64_t vs) {      // row strides (elements) of q, k, v; o is contiguous [T, nq, D]
     constexpr int CPR = D / 8;
     constexpr int Q_BYTES = PF_BQ * D * 2;
     constexpr int KV_BYTES = PF_BK * D * 2;
@@ -35,10 +36,10 @@ __global__ void __launch_bounds__(PF_THREADS, 1) prefill_attn_kernel(
     const int kvh = head / (nq / nkv);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
-    const T* qg = q + (tok0 * nq + head) * D;           // row stride nq*D
-    const T* kg = k + (tok0 * nkv + kvh) * D;           // row stride nkv*D
-    const T* vg = v + (tok0 * nkv + kvh) * D;
-    const int64_t qs = (int64_t)nq * D, kvs = (int64_t)nkv * D;
+    const T* qg = q + tok0 * qs + (int64_t)head * D;
+    const T* kg = k + tok0 * ks + (int64_t)kvh * D;
+    const T* vg = v + tok0 * vs + (int64_t)kvh * D;
+    const int64_t os = (int64_t)nq * D;
 
     const uint32_t q_sm = smem_u32(smem);
     auto kv_sm = [&](int stage) { return smem_u32(smem + Q_BYTES + stage * 2 * KV_BYTES); };
@@ -55,15 +56,15 @@ __global__ void __launch_bounds__(PF_THREADS, 1) prefill_attn_kernel(
     const int kv_end = min(len, q0 + PF_BQ);             // causal: keys < kv_end
     const int ntiles = (kv_end + PF_BK - 1) / PF_BK;
     auto issue_kv = [&](int tile) {
-        const uint32_t ks = kv_sm(tile & 1), vs = ks + KV_BYTES;
+        const uint32_t ksm = kv_sm(tile & 1), vsm = ksm + KV_BYTES;
 #pragma unroll
         for (int it = 0; it < PF_BK * CPR / PF_THREADS; it++) {
             const int idx = tid + it * PF_THREADS, r = idx / CPR, c = idx % CPR;
             const int t = tile * PF_BK + r;
             const bool valid = t < len;
-            const int64_t off = (int64_t)(valid ? t : 0) * kvs + c * 8;
-            cp_async16(ks + tile_off<D>(r, c), kg + off, valid ? 16 : 0);
-            cp_async16(vs + tile_off<D>(r, c), vg + off, valid ? 16 : 0);
+            const int64_t tr = valid ? t : 0;
+            cp_async16(ksm + tile_off<D>(r, c), kg + tr * ks + c * 8, valid ? 16 : 0);
+            cp_async16(vsm + tile_off<D>(r, c), vg + tr * vs + c * 8, valid ? 16 : 0);
         }
     };
     issue_kv(0);
@@ -172,15 +173,15 @@ __global__ void __launch_bounds__(PF_THREADS, 1) prefill_attn_kernel(
     const int c0 = (lane & 3) * 2;
 #pragma unroll
     for (int j = 0; j < D / 8; j++) {
-        if (row0 < len) *reinterpret_cast<uint32_t*>(og + (int64_t)row0 * qs + j * 8 + c0) = pack2<T>(o_acc[j][0] * i0, o_acc[j][1] * i0);
-        if (row1 < len) *reinterpret_cast<uint32_t*>(og + (int64_t)row1 * qs + j * 8 + c0) = pack2<T>(o_acc[j][2] * i1, o_acc[j][3] * i1);
+        if (row0 < len) *reinterpret_cast<uint32_t*>(og + (int64_t)row0 * os + j * 8 + c0) = pack2<T>(o_acc[j][0] * i0, o_acc[j][1] * i0);
+        if (row1 < len) *reinterpret_cast<uint32_t*>(og + (int64_t)row1 * os + j * 8 + c0) = pack2<T>(o_acc[j][2] * i1, o_acc[j][3] * i1);
     }
 }
 
 template <typename T, int D>
 static int launch_prefill(const void* q, const void* k, const void* v, void* o, const int32_t* start_locs,
                           const int32_t* seq_lens, float scale, int num_seqs, int max_len, int nq, int nkv,
-                          cudaStream_t stream) {
+                          int64_t qs, int64_t ks, int64_t vs, cudaStream_t stream) {
     const size_t smem = (size_t)PF_BQ * D * 2 + 2 * 2 * (size_t)PF_BK * D * 2;
     static bool configured = false;
     if (!configured) {
@@ -189,15 +190,15 @@ static int launch_prefill(const void* q, const void* k, const void* v, void* o, 
     }
     dim3 grid(cdiv(max_len, PF_BQ), nq, num_seqs);
     prefill_attn_kernel<T, D><<<grid, PF_THREADS, smem, stream>>>((const T*)q, (const T*)k, (const T*)v, (T*)o, start_locs,
-                                                                 seq_lens, scale * 1.4426950408889634f, nq, nkv);
+                                                                 seq_lens, scale * 1.4426950408889634f, nq, nkv, qs, ks, vs);
     return check_launch("prefill_attention");
 }
 
 // generation 2 (prefill_attn_tc.cu)
 bool tc_prefill_supported(int head_dim, int64_t num_tokens);
 int launch_prefill_tc(const void* q, const void* k, const void* v, void* o, const int32_t* start_locs, const int32_t* seq_lens,
-                      float scale_log2e, int num_seqs, int max_len, int64_t num_tokens, int nq, int nkv, sllm_dtype_t dtype,
-                      cudaStream_t stream);
+                      float scale_log2e, int num_seqs, int max_len, int64_t num_tokens, int nq, int nkv, int64_t qs, int64_t ks,
+                      int64_t vs, sllm_dtype_t dtype, cudaStream_t stream);
 
 }  // namespace sllm
 
@@ -206,21 +207,24 @@ using namespace sllm;
 extern "C" int sllm_prefill_attention(const void* q, const void* k, const void* v, void* o, const int32_t* start_locs,
                                       const int32_t* seq_lens, float softmax_scale, int num_prefill_seqs,
                                       int max_prefill_len, int64_t num_prefill_tokens, int nq, int nkv, int head_dim,
+                                      int64_t q_row_stride, int64_t k_row_stride, int64_t v_row_stride,
                                       sllm_dtype_t dtype, sllm_stream_t stream) {
     SLLM_REQUIRE(num_prefill_seqs >= 0 && max_prefill_len >= 0, "prefill_attention: negative sizes");
     if (num_prefill_seqs == 0 || max_prefill_len == 0) return 0;
     SLLM_REQUIRE(q && k && v && o && start_locs && seq_lens, "prefill_attention: null pointer");
     SLLM_REQUIRE(head_dim == 64 || head_dim == 128, "prefill_attention: head_dim %d not supported (64, 128)", head_dim);
     SLLM_REQUIRE(nkv > 0 && nq % nkv == 0, "prefill_attention: nq %d not a multiple of nkv %d", nq, nkv);
+    SLLM_REQUIRE(q_row_stride >= (int64_t)nq * head_dim && k_row_stride >= (int64_t)nkv * head_dim && v_row_stride >= (int64_t)nkv * head_dim &&
+                 q_row_stride % 8 == 0 && k_row_stride % 8 == 0 && v_row_stride % 8 == 0, "prefill_attention: bad row strides");
     cudaStream_t st = (cudaStream_t)stream;
     // SLLM_PREFILL_ATTN_GEN=1 forces the cp.async/mma.sync kernel (A/B measurements); default: tcgen05/TMA for head_dim 128
     const char* gen_env = getenv("SLLM_PREFILL_ATTN_GEN");
     const int gen = (gen_env && gen_env[0] == '1') ? 1 : (gen_env && gen_env[0] == '2') ? 2 : 0;
     if (gen != 1 && dtype <= SLLM_BF16 && tc_prefill_supported(head_dim, num_prefill_tokens))
         return launch_prefill_tc(q, k, v, o, start_locs, seq_lens, softmax_scale * 1.4426950408889634f, num_prefill_seqs,
-                                 max_prefill_len, num_prefill_tokens, nq, nkv, dtype, st);
+                                 max_prefill_len, num_prefill_tokens, nq, nkv, q_row_stride, k_row_stride, v_row_stride, dtype, st);
     SLLM_REQUIRE(gen != 2, "prefill_attention: SLLM_PREFILL_ATTN_GEN=2 but the shape is not covered by the tcgen05 kernel");
-    if (head_dim == 128) { SLLM_DISPATCH_DTYPE(dtype, return (launch_prefill<T, 128>(q, k, v, o, start_locs, seq_lens, softmax_scale, num_prefill_seqs, max_prefill_len, nq, nkv, st))); }
-    else { SLLM_DISPATCH_DTYPE(dtype, return (launch_prefill<T, 64>(q, k, v, o, start_locs, seq_lens, softmax_scale, num_prefill_seqs, max_prefill_len, nq, nkv, st))); }
+    if (head_dim == 128) { SLLM_DISPATCH_DTYPE(dtype, return (launch_prefill<T, 128>(q, k, v, o, start_locs, seq_lens, softmax_scale, num_prefill_seqs, max_prefill_len, nq, nkv, q_row_stride, k_row_stride, v_row_stride, st))); }
+    else { SLLM_DISPATCH_DTYPE(dtype, return (launch_prefill<T, 64>(q, k, v, o, start_locs, seq_lens, softmax_scale, num_prefill_seqs, max_prefill_len, nq, nkv, q_row_stride, k_row_stride, v_row_stride, st))); }
     return 0;
 }

@@ -321,13 +321,16 @@ __global__ void __launch_bounds__(PT_THREADS, 1) prefill_attn_tc_kernel(const __
 // ------------------------------------------------------------------ host side
 namespace {
 std::mutex g_pt_mutex;
-struct PtKey { const void* ptr; uint64_t rows; int cols; int dt; bool operator==(const PtKey& o) const { return ptr == o.ptr && rows == o.rows && cols == o.cols && dt == o.dt; } };
-struct PtKeyHash { size_t operator()(const PtKey& k) const { return std::hash<const void*>()(k.ptr) ^ (k.rows * 1315423911u) ^ (size_t)(k.cols * 31 + k.dt); } };
+struct PtKey {
+    const void* ptr; uint64_t rows; int cols; int dt; int64_t stride;
+    bool operator==(const PtKey& o) const { return ptr == o.ptr && rows == o.rows && cols == o.cols && dt == o.dt && stride == o.stride; }
+};
+struct PtKeyHash { size_t operator()(const PtKey& k) const { return std::hash<const void*>()(k.ptr) ^ (k.rows * 1315423911u) ^ (size_t)(k.cols * 31 + k.dt) ^ ((size_t)k.stride << 7); } };
 std::unordered_map<PtKey, CUtensorMap, PtKeyHash> g_pt_maps;
 
-// 2-D map over a packed [rows, cols] 16-bit tensor, boxes of (64 cols x box_rows), SWIZZLE_128B
-bool pt_map(CUtensorMap* out, const void* ptr, uint64_t rows, int cols, int box_rows, sllm_dtype_t dt) {
-    PtKey key{ptr, rows, cols * 1024 + box_rows, (int)dt};
+// 2-D map over a [rows, cols] 16-bit tensor with `row_stride` elements between rows, boxes of (64 cols x box_rows), SWIZZLE_128B
+bool pt_map(CUtensorMap* out, const void* ptr, uint64_t rows, int cols, int64_t row_stride, int box_rows, sllm_dtype_t dt) {
+    PtKey key{ptr, rows, cols * 1024 + box_rows, (int)dt, row_stride};
     {
         std::lock_guard<std::mutex> lk(g_pt_mutex);
         auto it = g_pt_maps.find(key);
@@ -336,7 +339,7 @@ bool pt_map(CUtensorMap* out, const void* ptr, uint64_t rows, int cols, int box_
     TensorMapEncodeFn enc = get_tensor_map_encoder();
     if (!enc) return false;
     cuuint64_t dims[2] = {(cuuint64_t)cols, rows};
-    cuuint64_t strides[1] = {(cuuint64_t)cols * 2};
+    cuuint64_t strides[1] = {(cuuint64_t)row_stride * 2};
     cuuint32_t box[2] = {64, (cuuint32_t)box_rows}, es[2] = {1, 1};
     CUresult r = enc(out, dt == SLLM_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr),
                      dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
@@ -354,12 +357,12 @@ bool tc_prefill_supported(int head_dim, int64_t num_tokens) {
 }
 
 int launch_prefill_tc(const void* q, const void* k, const void* v, void* o, const int32_t* start_locs, const int32_t* seq_lens,
-                      float scale_log2e, int num_seqs, int max_len, int64_t num_tokens, int nq, int nkv, sllm_dtype_t dtype,
-                      cudaStream_t stream) {
+                      float scale_log2e, int num_seqs, int max_len, int64_t num_tokens, int nq, int nkv, int64_t qs, int64_t ks,
+                      int64_t vs, sllm_dtype_t dtype, cudaStream_t stream) {
     CUtensorMap qmap, kmap, vmap;
-    SLLM_REQUIRE(pt_map(&qmap, q, (uint64_t)num_tokens, nq * PT_D, PT_BQ, dtype) &&
-                 pt_map(&kmap, k, (uint64_t)num_tokens, nkv * PT_D, PT_BK, dtype) &&
-                 pt_map(&vmap, v, (uint64_t)num_tokens, nkv * PT_D, PT_BK, dtype),
+    SLLM_REQUIRE(pt_map(&qmap, q, (uint64_t)num_tokens, nq * PT_D, qs, PT_BQ, dtype) &&
+                 pt_map(&kmap, k, (uint64_t)num_tokens, nkv * PT_D, ks, PT_BK, dtype) &&
+                 pt_map(&vmap, v, (uint64_t)num_tokens, nkv * PT_D, vs, PT_BK, dtype),
                  "prefill_attention: cuTensorMapEncodeTiled failed");
     PtParams p;
     p.o = o; p.start_locs = start_locs; p.seq_lens = seq_lens; p.scale_log2e = scale_log2e; p.nq = nq; p.nkv = nkv;

@@ -16,8 +16,7 @@ def store_kvcache(
     infer_state: LlamaInferState,
     cur_layer: int
 ):
-    assert k.is_contiguous()
-    assert v.is_contiguous()
+    ks, vs = _lib.row_stride(k), _lib.row_stride(v)      # contiguous (reference) or slices of a fused QKV output
     assert k_cache.is_contiguous()
     assert v_cache.is_contiguous()
     assert block_table.is_contiguous()
@@ -32,5 +31,5 @@ def store_kvcache(
         _lib.ptr(infer_state.prefill_seq_start_locs), _lib.ptr(infer_state.prefill_seq_lens),
         _lib.ptr(infer_state.decoding_seq_lens),
         infer_state.num_prefill_seqs, infer_state.num_decoding_seqs, infer_state.num_prefill_tokens,
-        infer_state.max_prefill_len, cur_layer, num_layers, nkv, bs, D, block_table.shape[1],
+        infer_state.max_prefill_len, cur_layer, num_layers, nkv, bs, D, block_table.shape[1], ks, vs,
         _lib.dtype_tag(k.dtype), _lib.stream()), "store_kvcache")

@@ -21,7 +21,7 @@ def paged_attention(
     cur_layer: int,
     o: torch.Tensor     # [num_decoding_seqs, num_q_heads*head_dim]
 ):
-    assert q.is_contiguous()
+    qs = _lib.row_stride(q)                              # contiguous (reference) or a slice of a fused QKV output
     assert k_cache.is_contiguous()
     assert v_cache.is_contiguous()
     assert block_table.is_contiguous()
@@ -45,7 +45,7 @@ def paged_attention(
         q.data_ptr(), k_cache.data_ptr(), v_cache.data_ptr(), block_table.data_ptr(), seq_ids.data_ptr(),
         infer_state.decoding_seq_lens.data_ptr(), o.data_ptr(), _lib.ptr(ws), ws_bytes,
         infer_state.softmax_scale, Bd, max_len, sbs, cur_layer, num_layers, nq, nkv, bs, D,
-        block_table.shape[1], num_blocks, _lib.dtype_tag(q.dtype), _lib.stream()), "paged_attention")
+        block_table.shape[1], num_blocks, qs, _lib.dtype_tag(q.dtype), _lib.stream()), "paged_attention")
     if TIMING_EVENTS is not None:
         ev1 = torch.cuda.Event(enable_timing=True); ev1.record()
         TIMING_EVENTS.append((ev0, ev1))

@@ -15,7 +15,8 @@ def prefill_attention(
     engine_config,
     infer_state: LlamaInferState,
 ):
-    assert q.is_contiguous() and k.is_contiguous() and v.is_contiguous() and o.is_contiguous()
+    assert o.is_contiguous()
+    qs, ks, vs = _lib.row_stride(q), _lib.row_stride(k), _lib.row_stride(v)
     _lib.require_device(q)
     Tp, nq, D = q.shape
     nkv = k.shape[1]
@@ -24,5 +25,5 @@ def prefill_attention(
     _lib.check(_lib.lib().sllm_prefill_attention(
         q.data_ptr(), k.data_ptr(), v.data_ptr(), o.data_ptr(),
         infer_state.prefill_seq_start_locs.data_ptr(), infer_state.prefill_seq_lens.data_ptr(),
-        infer_state.softmax_scale, infer_state.num_prefill_seqs, infer_state.max_prefill_len, Tp, nq, nkv, D,
+        infer_state.softmax_scale, infer_state.num_prefill_seqs, infer_state.max_prefill_len, Tp, nq, nkv, D, qs, ks, vs,
         _lib.dtype_tag(q.dtype), _lib.stream()), "prefill_attention")

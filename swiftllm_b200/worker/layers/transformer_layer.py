@@ -1,7 +1,7 @@
 """One Llama decoder layer.  Op sequence of the reference (swiftllm/worker/layers/transformer_layer.py:31-130):
 fused add+RMSNorm -> q/k/v GEMMs -> rotary -> KV store -> attention (prefill: causal varlen flash attention on the
 packed prompt tokens; decode: paged attention through the block table) -> o_proj -> fused add+RMSNorm ->
-up_gate GEMM -> SiLU*mul -> down GEMM.
+up_gate GEMM -> SiLU*mul -> down GEMM.  q/k/v come from ONE fused GEMM.
 
 Differences by design: the prefill attention is this library's own kernel (the reference calls third-party
 vllm_flash_attn, :86-96); with tensor parallelism each rank runs its head / FFN-column shard and the partial
@@ -51,9 +51,13 @@ class LlamaTransformerLayer:
         mc, w = self.model_config, self.weight
         fused_add_rmsnorm_inplace(input_embds, residual_buf, w.attn_norm, mc.rms_norm_eps)
 
-        q = linear(input_embds, w.q_proj).view(-1, self.num_q_heads, mc.head_dim)
-        k = linear(input_embds, w.k_proj).view(-1, self.num_kv_heads, mc.head_dim)
-        v = linear(input_embds, w.v_proj).view(-1, self.num_kv_heads, mc.head_dim)
+        # one GEMM for q, k and v (three latency-bound GEMMs in the reference, transformer_layer.py:54-56); the
+        # kernels below take the row-strided column slices directly
+        qkv = linear(input_embds, w.qkv_proj)
+        T, nqd, nkvd = qkv.shape[0], self.num_q_heads * mc.head_dim, self.num_kv_heads * mc.head_dim
+        q = qkv[:, :nqd].unflatten(1, (self.num_q_heads, mc.head_dim))
+        k = qkv[:, nqd:nqd + nkvd].unflatten(1, (self.num_kv_heads, mc.head_dim))
+        v = qkv[:, nqd + nkvd:].unflatten(1, (self.num_kv_heads, mc.head_dim))
 
         rotary_embedding_inplace(q, k, infer_state)
 

@@ -60,6 +60,13 @@ class LlamaTransformerLayerWeight:
         # up first, gate second (weight.py:133; silu_and_mul reads gate from the second half)
         self.up_gate_proj = torch.cat((self.up_proj, self.gate_proj), dim=0).contiguous()
         del self.up_proj, self.gate_proj
+        # q | k | v fused into one GEMM operand (the fusion the reference left commented out, weight.py:131-132);
+        # q_proj / k_proj / v_proj stay available as row views of it (no extra memory)
+        nq_rows, nkv_rows = self.q_proj.shape[0], self.k_proj.shape[0]
+        self.qkv_proj = torch.cat((self.q_proj, self.k_proj, self.v_proj), dim=0).contiguous()
+        self.q_proj = self.qkv_proj[:nq_rows]
+        self.k_proj = self.qkv_proj[nq_rows:nq_rows + nkv_rows]
+        self.v_proj = self.qkv_proj[nq_rows + nkv_rows:]
 
 
 class LlamaWeight:

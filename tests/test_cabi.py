@@ -37,7 +37,7 @@ def test_invalid_arguments_are_rejected_before_launch():
     l = _lib.lib()
     assert l.sllm_rmsnorm_inplace(None, None, 1e-5, 4, 12, 0, None) != 0         # hidden % 8 != 0
     assert b"multiple of 8" in l.sllm_last_error()
-    assert l.sllm_paged_attention(1, 1, 1, 1, 1, 1, 1, None, 0, 1.0, 1, 16, 0, 0, 1, 4, 2, 16, 96, 4, 4, 0, None) != 0
+    assert l.sllm_paged_attention(1, 1, 1, 1, 1, 1, 1, None, 0, 1.0, 1, 16, 0, 0, 1, 4, 2, 16, 96, 4, 4, 4 * 96, 0, None) != 0
     assert b"head_dim" in l.sllm_last_error()
     assert l.sllm_silu_and_mul_inplace(None, 0, 256, 7, None) == 0              # empty batch is a no-op
     assert l.sllm_swap_blocks(None, None, 0, 1, None, None, None, None, 16, None) == 0

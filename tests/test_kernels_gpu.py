@@ -471,3 +471,54 @@ def test_prefill_attention_long_sequence_property(prefill_gen):
     for r in (0, 1, 127, 128, 2047, 3000):
         rr = K.paged_attention_exact(q[r:r + 1], kc, vc, bt, [0], [r + 1], D ** -0.5, bs, 0)
         assert (o[r].reshape(-1).double() - rr[0]).abs().max() <= 8e-3 * max(rr.abs().max(), 1e-3)
+
+
+# ----------------------------------------------------------------------------- row-strided q/k/v (fused QKV GEMM output)
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_kernels_accept_fused_qkv_column_slices(dtype, paged_gen, prefill_gen):
+    """q, k, v as column slices of one [T, (nq + 2 nkv) D] buffer (what the fused QKV GEMM produces) must give exactly
+    the results of separate contiguous tensors: rotary, KV store, prefill attention, paged attention."""
+    from swiftllm_b200.worker.kernels.rotary_emb import rotary_embedding_inplace
+    from swiftllm_b200.worker.kernels.kvcache_mgmt import store_kvcache
+    from swiftllm_b200.worker.kernels.prefill_attn import prefill_attention
+    from swiftllm_b200.worker.kernels.paged_attn import paged_attention
+    nq, nkv, D, bs, L = 8, 2, 128, 16, 2
+    plens, dlens = [130, 17], [300, 45, 64]
+    Tp, Bd = sum(plens), len(dlens)
+    Tn = Tp + Bd
+    g = torch.Generator().manual_seed(21)
+    qkv = torch.randn(Tn, (nq + 2 * nkv) * D, generator=g).to(dtype).to(DEV)
+    def views(buf):
+        q = buf[:, : nq * D].unflatten(1, (nq, D)); k = buf[:, nq * D:(nq + nkv) * D].unflatten(1, (nkv, D))
+        v = buf[:, (nq + nkv) * D:].unflatten(1, (nkv, D))
+        return q, k, v
+    qs, ks, vs = views(qkv.clone())
+    qc, kc_, vc_ = [t.contiguous() for t in views(qkv.clone())]
+    ang = torch.rand(Tn, D // 2, generator=g) * 6.28
+    st_rot = NS(position_cos=torch.cos(ang).to(dtype).to(DEV), position_sin=torch.sin(ang).to(dtype).to(DEV))
+    rotary_embedding_inplace(qs, ks, st_rot); rotary_embedding_inplace(qc, kc_, st_rot)
+    assert torch.equal(qs, qc) and torch.equal(ks, kc_)
+    # block tables: prefill seqs 0,1 then decoding seqs 2,3,4 (their earlier tokens are random cache content)
+    need = [(n + bs - 1) // bs for n in plens + dlens]
+    nblk = sum(need) + 2
+    bt = torch.full((5, max(need)), -1, dtype=torch.int32); p = 0
+    for s_, n in enumerate(need):
+        bt[s_, :n] = torch.arange(p, p + n, dtype=torch.int32); p += n
+    bt = bt.to(DEV)
+    i32 = lambda x: torch.tensor(x, dtype=torch.int32, device=DEV)
+    st = NS(seq_ids=i32([0, 1, 2, 3, 4]), num_prefill_seqs=2, num_decoding_seqs=Bd, num_prefill_tokens=Tp,
+            prefill_seq_start_locs=i32([0, plens[0]]), prefill_seq_lens=i32(plens), max_prefill_len=max(plens),
+            decoding_seq_lens=i32(dlens), max_decoding_len=max(dlens), softmax_scale=D ** -0.5, paged_attn_seq_block_size=0)
+    cache0 = torch.randn(nblk, L, nkv, bs, D, generator=g).to(dtype).to(DEV)
+    k1, v1, k2, v2 = cache0.clone(), cache0.flip(0).clone(), cache0.clone(), cache0.flip(0).clone()
+    store_kvcache(ks, vs, k1, v1, bt, None, None, st, 1); store_kvcache(kc_, vc_, k2, v2, bt, None, None, st, 1)
+    assert torch.equal(k1, k2) and torch.equal(v1, v2)
+    o1 = torch.zeros(Tp, nq, D, dtype=dtype, device=DEV); o2 = torch.zeros_like(o1)
+    prefill_attention(qs[:Tp], ks[:Tp], vs[:Tp], o1, None, None, st); prefill_attention(qc[:Tp].contiguous(), kc_[:Tp].contiguous(), vc_[:Tp].contiguous(), o2, None, None, st)
+    assert torch.equal(o1, o2)
+    d1 = torch.zeros(Bd, nq * D, dtype=dtype, device=DEV); d2 = torch.zeros_like(d1)
+    paged_attention(qs[Tp:], k1, v1, bt, None, NS(block_size=bs), st, 1, d1)
+    paged_attention(qc[Tp:].contiguous(), k1, v1, bt, None, NS(block_size=bs), st, 1, d2)
+    assert torch.equal(d1, d2)
+    ref = K.paged_attention_exact(qc[Tp:].cpu(), k1.cpu(), v1.cpu(), bt.cpu(), [2, 3, 4], dlens, D ** -0.5, bs, 1)
+    assert (d1.cpu().double() - ref).abs().max() <= (2e-3 if dtype == torch.float16 else 1e-2) * ref.abs().max()
