@@ -174,7 +174,7 @@ def run_reference(args):
             "cpu_baseline": {"value": tok_s, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": tok_s, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0, "wall_s": time.perf_counter() - t0}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def workload_config(args, cfg, n):
@@ -368,7 +368,7 @@ def run_ours(args):
     }
     if args.layers:
         line["reduced"] = "layer count overridden: NOT a valid BASELINE measurement"
-    print(json.dumps(line), flush=True)
+    emit(line)
     _finish_distributed(model, n)
 
 
@@ -386,7 +386,25 @@ def _finish_distributed(model, n):
     os._exit(0)
 
 
+_REAL_STDOUT = None
+
+
+def _protect_stdout():
+    """The contract is ONE JSON line on stdout.  Libraries (NCCL's version banner, torchrun notices) write to fd 1
+    from C code, so point fd 1 at stderr for the whole run and keep a private duplicate for the result line."""
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+
+
+def emit(line: dict):
+    _REAL_STDOUT.write(json.dumps(line) + "\n")
+    _REAL_STDOUT.flush()
+
+
 def main():
+    _protect_stdout()
     args = parse()
     if args.impl == "reference":
         run_reference(args)
