@@ -124,6 +124,18 @@ int sllm_allocate_blocks_for_seqs(int32_t* num_seq_allocated_blocks, int32_t* bl
                                   int64_t* new_blocks_out, int64_t new_blocks_capacity, int32_t* status_out,
                                   sllm_stream_t stream);
 
+/* ---- Tensor-parallel exchange fused with the op that follows it (new; the reference is single-GPU):
+ *   residual <- h(sum over ranks of partial) + residual ;  x_out <- rmsnorm(residual) * weight
+ * i.e. the all-reduce after o_proj / down_proj merged with fused_add_rmsnorm_inplace (rmsnorm.py:67-89) in one kernel that
+ * reads every rank's partial [num_tokens, hidden] directly over NVLink peer memory, in rank order with fp32 accumulation
+ * (bit-identical on all ranks).  host_peer_bufs / host_peer_flags: HOST arrays of `nranks` DEVICE pointers: the partial buffer
+ * and the flag pad (uint32 [16 slots][8]) of every rank as mapped into this process (e.g. torch symmetric memory);
+ * epoch_state: local device memory, 32 uint32, zeroed once; slot: which of the alternating buffers / flag rows is used.
+ * weight == NULL skips the norm (x_out unused). */
+int sllm_allreduce_add_rmsnorm(const void* const* host_peer_bufs, void* const* host_peer_flags, int rank, int nranks,
+                               int slot, void* epoch_state, void* x_out, void* residual, const void* weight, float eps,
+                               int64_t num_tokens, int hidden, sllm_dtype_t dtype, sllm_stream_t stream);
+
 /* ---- Block swapping: csrc/src/block_swapping.cpp:22-85 (swiftllm_c.swap_blocks, csrc/src/entrypoints.cpp:5-7)
  * host_src_ids/host_dst_ids: HOST arrays of n block ids.  k_swap/v_swap: HOST memory (pinned or pageable),
  * k_cache/v_cache: device.  block_bytes = bytes of one block (all layers/heads) of k_cache.

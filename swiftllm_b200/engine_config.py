@@ -27,6 +27,7 @@ class EngineConfig:
     tp_rank: int = 0
     pin_swap_space: bool = True     # the reference's swap space is pageable (model.py:158-159)
     use_cuda_graph: bool = False    # capture pure-decode steps into CUDA graphs
+    fused_allreduce: bool = False   # TP: one-shot peer-memory all-reduce fused with add+RMSNorm instead of NCCL + a kernel
 
     @staticmethod
     def add_cli_args(parser: argparse.ArgumentParser):

@@ -13,7 +13,9 @@ class LlamaPostLayer:
         self.last_logits = None     # kept for parity tests (the reference discards them)
         self.keep_logits = False
 
-    def forward(self, input_embds: torch.Tensor, infer_state: LlamaInferState) -> torch.Tensor:
+    def forward(self, input_embds: torch.Tensor, infer_state: LlamaInferState, already_normed: bool = False) -> torch.Tensor:
+        """`already_normed`: input_embds rows are rmsnorm(final residual) already (TP fused-exchange path; RMSNorm is
+        row-wise, so normalising before or after the last-token gather is the same computation)."""
         idx = infer_state.last_token_indices
         if idx is None:
             idx = torch.cat((
@@ -21,7 +23,8 @@ class LlamaPostLayer:
                 torch.arange(infer_state.num_prefill_tokens, infer_state.num_tokens, device=input_embds.device, dtype=torch.int32)
             ), dim=0)
         last_input = input_embds.index_select(0, idx)          # [batch_size, hidden_size], fresh contiguous buffer
-        rmsnorm_inplace(last_input, self.weights.final_norm, self.model_config.rms_norm_eps)
+        if not already_normed:
+            rmsnorm_inplace(last_input, self.weights.final_norm, self.model_config.rms_norm_eps)
         logits = linear(last_input, self.weights.lm_head)      # [batch_size, vocab_size]
         if self.keep_logits:
             self.last_logits = logits

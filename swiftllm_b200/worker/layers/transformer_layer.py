@@ -23,7 +23,7 @@ from swiftllm_b200.worker.kernels.silu_and_mul import silu_and_mul_inplace
 
 class LlamaTransformerLayer:
     def __init__(self, model_config, engine_config, weight, decoding_piggyback_stream, layer_id: int,
-                 tp_group=None):
+                 tp_group=None, comm=None):
         self.model_config = model_config
         self.engine_config = engine_config
         self.weight = weight
@@ -31,6 +31,7 @@ class LlamaTransformerLayer:
         self.layer_id = layer_id
         self.tp_size = getattr(engine_config, "tp_size", 1)
         self.tp_group = tp_group
+        self.comm = comm            # FusedAllReduce (tp_comm.py) or None -> NCCL all-reduce + separate add/norm kernels
         self.num_q_heads = model_config.num_q_heads // self.tp_size      # per-rank shard
         self.num_kv_heads = model_config.num_kv_heads // self.tp_size
         self.ffn_inter_dim = model_config.ffn_inter_dim // self.tp_size
@@ -49,7 +50,12 @@ class LlamaTransformerLayer:
         infer_state: LlamaInferState,
     ) -> torch.Tensor:
         mc, w = self.model_config, self.weight
-        fused_add_rmsnorm_inplace(input_embds, residual_buf, w.attn_norm, mc.rms_norm_eps)
+        comm = self.comm
+        if comm is not None and self.layer_id > 0:
+            # the previous layer left its down_proj PARTIAL in symmetric buffer 1: exchange + add + norm in one kernel
+            input_embds = comm.reduce_add_norm(1, residual_buf.shape[0], residual_buf, w.attn_norm, mc.rms_norm_eps)
+        else:
+            fused_add_rmsnorm_inplace(input_embds, residual_buf, w.attn_norm, mc.rms_norm_eps)
 
         # one GEMM for q, k and v (three latency-bound GEMMs in the reference, transformer_layer.py:54-56); the
         # kernels below take the row-strided column slices directly
@@ -87,6 +93,16 @@ class LlamaTransformerLayer:
             else:
                 paged_attention(q[npt:], k_cache, v_cache, block_table, mc, self.engine_config, infer_state,
                                 self.layer_id, o[npt:])
+
+        if comm is not None:
+            T = o.shape[0]
+            torch.mm(o, w.o_proj.t(), out=comm.partial_out(0, T))              # partial sums -> symmetric buffer 0
+            o = comm.reduce_add_norm(0, T, residual_buf, w.ffn_norm, mc.rms_norm_eps)
+            up_gate_proj = linear(o, w.up_gate_proj)
+            silu_and_mul_inplace(up_gate_proj)
+            ffn_out = comm.partial_out(1, T)                                   # consumed by the next layer / the model tail
+            torch.mm(up_gate_proj[:, :self.ffn_inter_dim], w.down_proj.t(), out=ffn_out)
+            return ffn_out
 
         o = linear(o, w.o_proj)                # row-parallel under TP: partial sums
         self._all_reduce(o)

@@ -114,11 +114,16 @@ class LlamaModel:
         cos, sin = build_rope_tables(self.model_config, self.dtype)
         self._cos_cached, self._sin_cached = cos.to(self.device), sin.to(self.device)
 
+        self.comm = None
+        if self.tp_size > 1 and getattr(self.engine_config, "fused_allreduce", False):
+            from swiftllm_b200.worker.tp_comm import FusedAllReduce
+            self.comm = FusedAllReduce(self.engine_config.max_tokens_in_batch, self.model_config.hidden_size, self.dtype,
+                                       self.device, self.tp_group)
         decoding_piggyback_stream = torch.cuda.Stream()
         self.pre_layer = LlamaPreLayer(self.model_config, self.weight)
         self.transformer_layers = [
             LlamaTransformerLayer(self.model_config, self.engine_config, self.weight.layers[i],
-                                  decoding_piggyback_stream, i, tp_group=self.tp_group)
+                                  decoding_piggyback_stream, i, tp_group=self.tp_group, comm=self.comm)
             for i in range(self.model_config.num_layers)
         ]
         self.post_layer = LlamaPostLayer(self.model_config, self.weight)
@@ -183,6 +188,11 @@ class LlamaModel:
             block_table = self.gpu_block_manager.block_table
         for layer in self.transformer_layers:
             input_embds = layer.forward(input_embds, residual_buf, k_cache, v_cache, block_table, infer_state)
+        if self.comm is not None:
+            # the last layer's down_proj partials are still un-reduced: exchange + add + final RMSNorm in one kernel
+            normed = self.comm.reduce_add_norm(1, residual_buf.shape[0], residual_buf, self.weight.final_norm,
+                                               self.model_config.rms_norm_eps)
+            return self.post_layer.forward(normed, infer_state, already_normed=True)
         input_embds += residual_buf
         return self.post_layer.forward(input_embds, infer_state)
 

@@ -1,0 +1,58 @@
+"""Tensor-parallel exchange over NVLink peer memory, fused with the residual add + RMSNorm that follows it
+(SURVEY.md §8 f-3).  torch.distributed symmetric memory is the plumbing (buffer allocation + handle exchange); the
+data movement and the reduction are this library's own kernel (`sllm_allreduce_add_rmsnorm`, csrc/allreduce_norm.cu).
+
+Two symmetric buffers alternate: slot 0 holds the o_proj partials, slot 1 the down_proj partials of a layer.  The GEMM
+writes its partial straight into the symmetric buffer (`torch.mm(..., out=)`), the fused kernel of every rank then reads
+all ranks' partials in rank order (bit-identical sums everywhere) and produces the normalised activations for the next
+GEMM.  NCCL all-reduce + fused_add_rmsnorm (the default path) computes the same thing in two launches.
+"""
+from __future__ import annotations
+
+import ctypes
+
+import torch
+import torch.distributed as dist
+
+from swiftllm_b200 import _lib
+
+NUM_SLOTS = 2
+
+
+class FusedAllReduce:
+    def __init__(self, max_tokens: int, hidden: int, dtype: torch.dtype, device, group=None):
+        import torch.distributed._symmetric_memory as symm_mem
+        group = group if group is not None else dist.group.WORLD
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        assert 2 <= self.world <= 8
+        self.max_tokens, self.hidden, self.dtype, self.device = max_tokens, hidden, dtype, device
+        try:
+            symm_mem.enable_symm_mem_for_group(group.group_name)      # needed by older torch, harmless otherwise
+        except Exception:       # noqa: BLE001
+            pass
+        self.data = symm_mem.empty((NUM_SLOTS, max_tokens, hidden), dtype=dtype, device=device)
+        self.flags = symm_mem.empty((16 * 8,), dtype=torch.int32, device=device)
+        self.data.zero_(); self.flags.zero_()
+        self._hd = symm_mem.rendezvous(self.data, group)
+        self._hf = symm_mem.rendezvous(self.flags, group)
+        torch.cuda.synchronize(); dist.barrier(group)                  # every rank's flags are zero before first use
+        slot_bytes = max_tokens * hidden * self.data.element_size()
+        PtrArr = ctypes.c_void_p * self.world
+        self._buf_ptrs = [PtrArr(*[int(p) + s * slot_bytes for p in self._hd.buffer_ptrs]) for s in range(NUM_SLOTS)]
+        self._flag_ptrs = PtrArr(*[int(p) for p in self._hf.buffer_ptrs])
+        self.epoch = torch.zeros((32,), dtype=torch.int32, device=device)
+
+    def partial_out(self, slot: int, num_tokens: int) -> torch.Tensor:
+        """The [num_tokens, hidden] view of this rank's symmetric buffer that the row-parallel GEMM must write into."""
+        assert num_tokens <= self.max_tokens
+        return self.data[slot, :num_tokens]
+
+    def reduce_add_norm(self, slot: int, num_tokens: int, residual: torch.Tensor, weight: torch.Tensor, eps: float) -> torch.Tensor:
+        """residual <- h(sum_ranks partial[slot]) + residual;  returns rmsnorm(residual) * weight (new tensor)."""
+        assert residual.is_contiguous() and residual.shape == (num_tokens, self.hidden)
+        out = torch.empty_like(residual)
+        _lib.check(_lib.lib().sllm_allreduce_add_rmsnorm(
+            ctypes.cast(self._buf_ptrs[slot], ctypes.c_void_p), ctypes.cast(self._flag_ptrs, ctypes.c_void_p),
+            self.rank, self.world, slot, self.epoch.data_ptr(), out.data_ptr(), residual.data_ptr(), weight.data_ptr(),
+            eps, num_tokens, self.hidden, _lib.dtype_tag(self.dtype), _lib.stream()), "allreduce_add_rmsnorm")
+        return out

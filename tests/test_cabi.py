@@ -17,7 +17,8 @@ def test_header_declares_expected_surface():
     for n in ["sllm_rmsnorm_inplace", "sllm_fused_add_rmsnorm_inplace", "sllm_rotary_embedding_inplace",
               "sllm_silu_and_mul_inplace", "sllm_store_kvcache", "sllm_paged_attention", "sllm_prefill_attention",
               "sllm_set_block_table_and_num_seq_alloc_blocks", "sllm_unset_block_table_and_num_seq_alloc_blocks",
-              "sllm_gather_allocated_blocks_and_unset", "sllm_allocate_blocks_for_seqs", "sllm_swap_blocks"]:
+              "sllm_gather_allocated_blocks_and_unset", "sllm_allocate_blocks_for_seqs", "sllm_swap_blocks",
+              "sllm_allreduce_add_rmsnorm"]:
         assert n in names
 
 

@@ -22,17 +22,18 @@ def _run(rank, world, port, q):
     torch.cuda.set_device(rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
 
-    def make(tp, r, graph=False):
+    def make(tp, r, graph=False, fused=False):
         ec = swiftllm_b200.EngineConfig(model_path="", use_dummy=False, block_size=16, gpu_mem_utilization=0.9, num_cpu_blocks=2,
                                         max_seqs_in_block_table=8, max_blocks_per_seq=16, max_batch_size=4, max_tokens_in_batch=256,
-                                        dtype="bfloat16", tp_size=tp, tp_rank=r, use_cuda_graph=graph)
+                                        dtype="bfloat16", tp_size=tp, tp_rank=r, use_cuda_graph=graph, fused_allreduce=fused)
         m = swiftllm_b200.LlamaModel(ec, swiftllm_b200.LlamaModelConfig(CFG))
         m.load_weights(synthetic_getter(seed=11, std=0.05, device=f"cuda:{rank}"))
         m.init_kvcache_and_swap(40)
         m.post_layer.keep_logits = True
         return m
-    tp = make(world, rank)
-    tpg = make(world, rank, graph=True)
+    fused = os.environ.get("SLLM_TEST_FUSED_AR", "0") == "1"
+    tp = make(world, rank, fused=fused)
+    tpg = make(world, rank, graph=True, fused=fused)
     ref = make(1, 0) if rank == 0 else None
     rng = np.random.default_rng(3)
     prompts = [rng.integers(0, 1000, size=n).tolist() for n in (40, 7, 129)]
@@ -75,14 +76,16 @@ def _run(rank, world, port, q):
     os._exit(0)
 
 
+@pytest.mark.parametrize("fused", [False, True], ids=["nccl", "fused-p2p"])
 @pytest.mark.parametrize("world", [2, 4])
-def test_tp_matches_single_gpu(world):
+def test_tp_matches_single_gpu(world, fused, monkeypatch):
     if torch.cuda.device_count() < world:
         pytest.skip(f"needs {world} GPUs")
+    monkeypatch.setenv("SLLM_TEST_FUSED_AR", "1" if fused else "0")
     import torch.multiprocessing as mp
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    procs = [ctx.Process(target=_run, args=(r, world, 29650 + world, q)) for r in range(world)]
+    procs = [ctx.Process(target=_run, args=(r, world, 29650 + world + (10 if fused else 0), q)) for r in range(world)]
     for p in procs:
         p.start()
     worst = q.get(timeout=300)
