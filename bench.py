@@ -47,8 +47,10 @@ def parse():
     ap.add_argument("--model", type=str, default="llama3-8b", choices=["llama3-8b", "llama3-70b", "tiny"])
     ap.add_argument("--layers", type=int, default=0, help="override the layer count (debug only; marks the run reduced)")
     ap.add_argument("--no-graph", action="store_true")
-    ap.add_argument("--fused-allreduce", action="store_true",
-                    help="TP: one-shot peer-memory all-reduce fused with add+RMSNorm instead of NCCL all-reduce + kernel")
+    ap.add_argument("--fused-allreduce", dest="fused_allreduce", action="store_true", default=None,
+                    help="TP: force the one-shot peer-memory all-reduce fused with add+RMSNorm (default: automatic, tp 2..4)")
+    ap.add_argument("--nccl-allreduce", dest="fused_allreduce", action="store_false",
+                    help="TP: force NCCL all-reduce + separate add/norm kernel")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-prefill", action="store_true")
     ap.add_argument("--cpu-sample-seqs", type=int, default=8)
@@ -183,7 +185,7 @@ def workload_config(args, cfg, n):
     return {"workload": f"{args.model} pure decode, batch {args.batch}, seq_len {args.seqlen}, block_size 16 "
                         f"(BASELINE.json configs[1])",
             "layers": cfg["num_hidden_layers"], "global_batch": args.batch, "seq_len": args.seqlen,
-            "parallelism": f"tp{n}" + ("+fused-allreduce" if getattr(args, "fused_allreduce", False) and n > 1 else ""), "l2": "inputs larger than L2 (KV working set and weights >> 126 MB)"}
+            "parallelism": f"tp{n}", "l2": "inputs larger than L2 (KV working set and weights >> 126 MB)"}
 
 
 # --------------------------------------------------------------------------- GPU arm
@@ -211,8 +213,8 @@ def run_ours(args):
     blocks_per_seq = (S + bs - 1) // bs
     ec = swiftllm_b200.EngineConfig(model_path="", use_dummy=False, block_size=bs, gpu_mem_utilization=0.97, num_cpu_blocks=0,
                                     max_seqs_in_block_table=B, max_blocks_per_seq=blocks_per_seq + 8, max_batch_size=B,
-                                    max_tokens_in_batch=max(B, 8192), dtype="bfloat16", tp_size=n, tp_rank=rank,
-                                    use_cuda_graph=not args.no_graph, fused_allreduce=args.fused_allreduce and n > 1)
+                                    max_tokens_in_batch=max(B, 16384), dtype="bfloat16", tp_size=n, tp_rank=rank,
+                                    use_cuda_graph=not args.no_graph, fused_allreduce=args.fused_allreduce)
     model = swiftllm_b200.LlamaModel(ec, mc)
     model.load_weights(synthetic_getter(seed=0, std=0.02, device=dev))
     num_blocks = B * blocks_per_seq + 64
@@ -364,6 +366,8 @@ def run_ours(args):
                      "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": alg_bytes, "mean_launch_ms": pa_ms, "launches_timed": len(durs),
                      "how": "CUDA events around every paged_attention launch over K eager decode steps on the launching stream"},
+        "tp_exchange": None if n == 1 else ("fused peer-memory all-reduce + add + rmsnorm (one kernel)" if model.comm is not None
+                                            else "ncclAllReduce + fused_add_rmsnorm"),
         "clocks": clk,
         "cpu_baseline": cpu,
         "prefill": prefill,

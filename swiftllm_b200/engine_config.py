@@ -27,7 +27,9 @@ class EngineConfig:
     tp_rank: int = 0
     pin_swap_space: bool = True     # the reference's swap space is pageable (model.py:158-159)
     use_cuda_graph: bool = False    # capture pure-decode steps into CUDA graphs
-    fused_allreduce: bool = False   # TP: one-shot peer-memory all-reduce fused with add+RMSNorm instead of NCCL + a kernel
+    # TP exchange: True = one-shot peer-memory all-reduce fused with add+RMSNorm (tp_comm.py), False = NCCL all-reduce +
+    # a separate kernel, None = automatic (fused for tp_size 2..4 where it was measured faster, NCCL otherwise)
+    fused_allreduce: object = None
 
     @staticmethod
     def add_cli_args(parser: argparse.ArgumentParser):

@@ -26,10 +26,6 @@ class FusedAllReduce:
         self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
         assert 2 <= self.world <= 8
         self.max_tokens, self.hidden, self.dtype, self.device = max_tokens, hidden, dtype, device
-        try:
-            symm_mem.enable_symm_mem_for_group(group.group_name)      # needed by older torch, harmless otherwise
-        except Exception:       # noqa: BLE001
-            pass
         self.data = symm_mem.empty((NUM_SLOTS, max_tokens, hidden), dtype=dtype, device=device)
         self.flags = symm_mem.empty((16 * 8,), dtype=torch.int32, device=device)
         self.data.zero_(); self.flags.zero_()
