@@ -143,6 +143,17 @@ __global__ void __launch_bounds__(PT_THREADS, 1) prefill_attn_tc_kernel(const __
         if (lane == 0) {
             constexpr uint32_t IDESC_S = make_instr_desc(128, PT_BK, UmmaFmt<T>::value, 0, 0);
             constexpr uint32_t IDESC_O = make_instr_desc(128, PT_D, UmmaFmt<T>::value, 0, 1);      // B = V, MN-major
+            // Descriptor bases are loop invariants: build them once; per UMMA only the 14-bit address field (16-byte units,
+            // low word) advances by a compile-time constant (all tiles live below 256 KiB, so no carry into the LBO field).
+            uint64_t dq[2], dk[PT_STAGES], dv[PT_STAGES], dp[2][2];
+            for (int x = 0; x < 2; x++) {
+                dq[x] = make_smem_desc(smem_u32(q_sm + x * PT_Q_BYTES), 16, 1024);
+                for (int b = 0; b < 2; b++) dp[x][b] = make_smem_desc(smem_u32(p_sm + (x * 2 + b) * PT_P_BYTES), 16, 1024);
+            }
+            for (int st = 0; st < PT_STAGES; st++) {
+                dk[st] = make_smem_desc(smem_u32(k_sm + st * PT_KV_BYTES), 16, 1024);
+                dv[st] = make_smem_desc(smem_u32(v_sm + st * PT_KV_BYTES), PT_KV_BYTES / 2, 1024);      // MN-major: LBO = d-half stride
+            }
             mbar_wait(smem_u32(&bars->q_full), 0);
             int js = 0, jp[2] = {0, 0};
             const int nk[2] = {nkt_a, nkt_b};
@@ -157,15 +168,14 @@ __global__ void __launch_bounds__(PT_THREADS, 1) prefill_attn_tc_kernel(const __
                         (!ua || mbar_test_wait(smem_u32(&bars->s_empty[0]), spar)) &&
                         (!ub || mbar_test_wait(smem_u32(&bars->s_empty[1]), spar))) {
                         tc_fence_after();
-                        const uint32_t kbase = smem_u32(k_sm + st * PT_KV_BYTES);
+                        const uint64_t kd = dk[st];
                         for (int x = 0; x < 2; x++) {
                             if (!(x == 0 ? ua : ub)) continue;
-                            const uint32_t qbase = smem_u32(q_sm + x * PT_Q_BYTES);
+                            const uint64_t qd = dq[x];
 #pragma unroll
-                            for (int ks = 0; ks < 8; ks++) {
-                                const uint64_t a = make_smem_desc(qbase + (ks >> 2) * (PT_Q_BYTES / 2) + (ks & 3) * 32, 16, 1024);
-                                const uint64_t b = make_smem_desc(kbase + (ks >> 2) * (PT_KV_BYTES / 2) + (ks & 3) * 32, 16, 1024);
-                                umma_ss(tmem + x * 64, a, b, IDESC_S, ks > 0);
+                            for (int ks = 0; ks < 8; ks++) {      // 16 d per UMMA; d-half = ks / 4
+                                umma_ss(tmem + x * 64, qd + (uint64_t)(((ks >> 2) * (PT_Q_BYTES / 2) + (ks & 3) * 32) >> 4),
+                                        kd + (uint64_t)(((ks >> 2) * (PT_KV_BYTES / 2) + (ks & 3) * 32) >> 4), IDESC_S, ks > 0);
                             }
                             umma_commit(smem_u32(&bars->s_full[x]));
                         }
@@ -182,14 +192,11 @@ __global__ void __launch_bounds__(PT_THREADS, 1) prefill_attn_tc_kernel(const __
                     if (mbar_test_wait(smem_u32(&bars->p_full[x][pb]), (j >> 1) & 1) &&
                         mbar_test_wait(smem_u32(&bars->v_full[st]), (j / PT_STAGES) & 1)) {
                         tc_fence_after();
-                        const uint32_t vbase = smem_u32(v_sm + st * PT_KV_BYTES);
-                        const uint32_t pbase = smem_u32(p_sm + (x * 2 + pb) * PT_P_BYTES);
+                        const uint64_t vd = dv[st], pd = dp[x][pb];
 #pragma unroll
-                        for (int kt = 0; kt < 4; kt++) {       // 16 tokens per UMMA
-                            const uint64_t a = make_smem_desc(pbase + kt * 32, 16, 1024);
-                            const uint64_t b = make_smem_desc(vbase + kt * 2048, PT_KV_BYTES / 2, 1024);
-                            umma_ss(tmem + 128 + x * 128, a, b, IDESC_O, (j > 0 || kt > 0) ? 1u : 0u);
-                        }
+                        for (int kt = 0; kt < 4; kt++)       // 16 tokens per UMMA
+                            umma_ss(tmem + 128 + x * 128, pd + (uint64_t)((kt * 32) >> 4), vd + (uint64_t)((kt * 2048) >> 4), IDESC_O,
+                                    (j > 0 || kt > 0) ? 1u : 0u);
                         umma_commit(smem_u32(&bars->p_empty[x][pb]));
                         // the V stage is free once every tile that uses it has issued its PV
                         const int other = 1 - x;
@@ -218,25 +225,36 @@ __global__ void __launch_bounds__(PT_THREADS, 1) prefill_attn_tc_kernel(const __
             tc_fence_after();
             uint32_t r0[32], r1[32];
             tmem_ld32(s_addr, r0);
-            tmem_ld32(s_addr + 32, r1);
             tmem_ld_wait();
-            tc_fence_before();
-            mbar_arrive(smem_u32(&bars->s_empty[x]));
+            tmem_ld32(s_addr + 32, r1);                            // in flight while the first half is reduced
 
             const int c0 = j * PT_BK;
             const bool need_mask = c0 + PT_BK - 1 > q0 + x * PT_BQ || c0 + PT_BK > len;
-            float mx = -INFINITY;                                  // max of the RAW scores (scale > 0 commutes with max)
+            // column c0+i is visible iff c0+i <= qi and c0+i < len  <=>  i <= lim   (branch-free selects)
+            const int lim = min(qi, len - 1) - c0;
+            float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;   // 4 independent chains
             if (need_mask) {
-                // column c0+i is visible iff c0+i <= qi and c0+i < len  <=>  i <= lim   (branch-free selects)
-                const int lim = min(qi, len - 1) - c0;
 #pragma unroll
-                for (int i = 0; i < 32; i++) {
-                    r0[i] = i <= lim ? r0[i] : 0xff800000u;        // -inf
-                    r1[i] = i + 32 <= lim ? r1[i] : 0xff800000u;
-                }
+                for (int i = 0; i < 32; i++) r0[i] = i <= lim ? r0[i] : 0xff800000u;        // -inf
             }
 #pragma unroll
-            for (int i = 0; i < 32; i++) mx = fmaxf(mx, fmaxf(__uint_as_float(r0[i]), __uint_as_float(r1[i])));
+            for (int i = 0; i < 32; i += 4) {
+                mx0 = fmaxf(mx0, __uint_as_float(r0[i])); mx1 = fmaxf(mx1, __uint_as_float(r0[i + 1]));
+                mx2 = fmaxf(mx2, __uint_as_float(r0[i + 2])); mx3 = fmaxf(mx3, __uint_as_float(r0[i + 3]));
+            }
+            tmem_ld_wait();
+            tc_fence_before();
+            mbar_arrive(smem_u32(&bars->s_empty[x]));
+            if (need_mask) {
+#pragma unroll
+                for (int i = 0; i < 32; i++) r1[i] = i + 32 <= lim ? r1[i] : 0xff800000u;
+            }
+#pragma unroll
+            for (int i = 0; i < 32; i += 4) {
+                mx0 = fmaxf(mx0, __uint_as_float(r1[i])); mx1 = fmaxf(mx1, __uint_as_float(r1[i + 1]));
+                mx2 = fmaxf(mx2, __uint_as_float(r1[i + 2])); mx3 = fmaxf(mx3, __uint_as_float(r1[i + 3]));
+            }
+            const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));       // max of the RAW scores (scale > 0 commutes with max)
             const float m_new = fmaxf(m_ref, mx * p.scale_log2e);
             // Lazy rescale.  The decision is per row, but tcgen05.ld/st are warp-collective (.sync.aligned): vote, and
             // let rows that do not need it take part with alpha = 1.
@@ -264,7 +282,7 @@ __global__ void __launch_bounds__(PT_THREADS, 1) prefill_attn_tc_kernel(const __
             const int pb = j & 1;
             if (j >= 2) mbar_wait(smem_u32(&bars->p_empty[x][pb]), ((j - 2) >> 1) & 1);
             // p = exp2(s*c - m_ref) (<= 2^8), row sum in fp32, P row -> shared memory ([128 rows][128 B], SWIZZLE_128B)
-            float ls = 0.f;
+            float ls0 = 0.f, ls1 = 0.f;
             const float neg_m = -m_ref, c = p.scale_log2e;
             uint8_t* prow = p_sm + (x * 2 + pb) * PT_P_BYTES + row * 128;
 #pragma unroll
@@ -275,13 +293,13 @@ __global__ void __launch_bounds__(PT_THREADS, 1) prefill_attn_tc_kernel(const __
                     const int i = ch * 8 + e * 2;                  // token pair (i, i+1) of this 64-token step
                     const float a = fast_exp2_tc(fmaf(__uint_as_float(i < 32 ? r0[i] : r1[i - 32]), c, neg_m));
                     const float b = fast_exp2_tc(fmaf(__uint_as_float(i + 1 < 32 ? r0[i + 1] : r1[i + 1 - 32]), c, neg_m));
-                    ls += a + b;
+                    ls0 += a; ls1 += b;
                     typename Traits<T>::T2 v2 = Traits<T>::from_f2(make_float2(a, b));
                     w[e] = *reinterpret_cast<uint32_t*>(&v2);
                 }
                 *reinterpret_cast<uint4*>(prow + ((ch ^ (row & 7)) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
             }
-            l += ls;
+            l += ls0 + ls1;
             fence_proxy_async();
             mbar_arrive(smem_u32(&bars->p_full[x][pb]));
         }
