@@ -4,9 +4,9 @@
 // swiftllm/worker/layers/transformer_layer.py:86-96.  head_dim 128, fp16/bf16; numerics per SURVEY.md Appendix A6
 // (fp32 scores, exp2 online softmax in fp32, P rounded to the storage dtype before P.V, o = h(acc / l)).
 //
-// CTA = (sequence, q head, 256 query rows) = two 128-row tiles A and B.  320 threads:
-//   warp 0      TMA producer: Q (4 boxes of 128 rows x 64 d) once, then per 64-token step one K tile and one V tile
-//               (2 boxes of 64 x 64 each) into 2-stage rings, K and V on separate mbarriers.
+// CTA = (sequence, q head, 256 query rows) = two 128-row tiles A and B.  352 threads:
+//   warp 0/10   TMA producers: warp 0 loads Q (4 boxes of 128 rows x 64 d) once and then the K tiles, warp 10 the V tiles
+//               (2 boxes of 64 x 64 per 64-token step) into separate 3-stage rings with their own mbarriers.
 //   warp 1      MMA issuer (one thread, polling):  S_X[128 x 64] = Q_X . K_j^T       (8 UMMAs, M=128 N=64 K=16)
 //                                                   O_X[128 x 128] += P_X . V_j       (4 UMMAs, M=128 N=128 K=16, B MN-major)
 //               S_A, S_B (64 TMEM columns each) and O_A, O_B (128 columns each) live in TMEM.
@@ -28,8 +28,8 @@ using namespace tc;
 constexpr int PT_D = 128;
 constexpr int PT_BQ = 128;                // rows per query tile (two tiles per CTA)
 constexpr int PT_BK = 64;                 // kv tokens per pipeline step
-constexpr int PT_STAGES = 2;
-constexpr int PT_THREADS = 320;
+constexpr int PT_STAGES = 3;               // K and V rings (separate producers): two steps of prefetch ahead of the MMA
+constexpr int PT_THREADS = 352;            // warp 0 K+Q producer, 1 MMA, 2-5 softmax A, 6-9 softmax B, 10 V producer
 constexpr int PT_Q_BYTES = PT_BQ * PT_D * 2;          // 32 KiB per query tile ([half][128 rows][128 B])
 constexpr int PT_KV_BYTES = PT_BK * PT_D * 2;         // 16 KiB per K (or V) tile ([half][64 rows][128 B])
 constexpr int PT_P_BYTES = PT_BQ * PT_BK * 2;         // 16 KiB per P tile ([128 rows][128 B])
@@ -115,7 +115,7 @@ __global__ void __launch_bounds__(PT_THREADS, 1) prefill_attn_tc_kernel(const __
     const uint32_t tmem = *tmem_base_s;
 
     if (warp == 0) {
-        // =========================================================== TMA producer
+        // =========================================================== TMA producer: Q once, then the K tiles
         if (lane == 0) {
             const uint32_t qbar = smem_u32(&bars->q_full);
             mbar_arrive_expect_tx(qbar, 2 * PT_Q_BYTES);
@@ -125,13 +125,19 @@ __global__ void __launch_bounds__(PT_THREADS, 1) prefill_attn_tc_kernel(const __
                                 tok0 + q0 + x * PT_BQ);
             for (int j = 0; j < nkt; j++) {
                 const int st = j % PT_STAGES;
-                const uint32_t par = ((j / PT_STAGES) & 1) ^ 1;
-                mbar_wait(smem_u32(&bars->k_empty[st]), par);
+                mbar_wait(smem_u32(&bars->k_empty[st]), ((j / PT_STAGES) & 1) ^ 1);
                 const uint32_t kb = smem_u32(&bars->k_full[st]);
                 mbar_arrive_expect_tx(kb, PT_KV_BYTES);
                 tma_load_2d(smem_u32(k_sm + st * PT_KV_BYTES), &kmap, kb, kvh * PT_D, tok0 + j * PT_BK);
                 tma_load_2d(smem_u32(k_sm + st * PT_KV_BYTES + PT_KV_BYTES / 2), &kmap, kb, kvh * PT_D + 64, tok0 + j * PT_BK);
-                mbar_wait(smem_u32(&bars->v_empty[st]), par);
+            }
+        }
+    } else if (warp == 10) {
+        // =========================================================== TMA producer: the V tiles (independent of K's progress)
+        if (lane == 0) {
+            for (int j = 0; j < nkt; j++) {
+                const int st = j % PT_STAGES;
+                mbar_wait(smem_u32(&bars->v_empty[st]), ((j / PT_STAGES) & 1) ^ 1);
                 const uint32_t vb = smem_u32(&bars->v_full[st]);
                 mbar_arrive_expect_tx(vb, PT_KV_BYTES);
                 tma_load_2d(smem_u32(v_sm + st * PT_KV_BYTES), &vmap, vb, kvh * PT_D, tok0 + j * PT_BK);
@@ -225,8 +231,10 @@ __global__ void __launch_bounds__(PT_THREADS, 1) prefill_attn_tc_kernel(const __
             tc_fence_after();
             uint32_t r0[32], r1[32];
             tmem_ld32(s_addr, r0);
+            tmem_ld32(s_addr + 32, r1);
             tmem_ld_wait();
-            tmem_ld32(s_addr + 32, r1);                            // in flight while the first half is reduced
+            tc_fence_before();
+            mbar_arrive(smem_u32(&bars->s_empty[x]));              // S buffer free: the next S UMMAs may overwrite it
 
             const int c0 = j * PT_BK;
             const bool need_mask = c0 + PT_BK - 1 > q0 + x * PT_BQ || c0 + PT_BK > len;
@@ -242,9 +250,6 @@ __global__ void __launch_bounds__(PT_THREADS, 1) prefill_attn_tc_kernel(const __
                 mx0 = fmaxf(mx0, __uint_as_float(r0[i])); mx1 = fmaxf(mx1, __uint_as_float(r0[i + 1]));
                 mx2 = fmaxf(mx2, __uint_as_float(r0[i + 2])); mx3 = fmaxf(mx3, __uint_as_float(r0[i + 3]));
             }
-            tmem_ld_wait();
-            tc_fence_before();
-            mbar_arrive(smem_u32(&bars->s_empty[x]));
             if (need_mask) {
 #pragma unroll
                 for (int i = 0; i < 32; i++) r1[i] = i + 32 <= lim ? r1[i] : 0xff800000u;
