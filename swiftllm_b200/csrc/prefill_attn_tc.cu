@@ -145,74 +145,88 @@ __global__ void __launch_bounds__(PT_THREADS, 1) prefill_attn_tc_kernel(const __
             }
         }
     } else if (warp == 1) {
-        // =========================================================== MMA issuer (one thread, polling three queues)
-        if (lane == 0) {
+        // =========================================================== MMA issuer: the whole warp runs the polling loop
+        // converged (votes make the control flow provably uniform); one elected lane issues the UMMAs and commits.
+        {
             constexpr uint32_t IDESC_S = make_instr_desc(128, PT_BK, UmmaFmt<T>::value, 0, 0);
             constexpr uint32_t IDESC_O = make_instr_desc(128, PT_D, UmmaFmt<T>::value, 0, 1);      // B = V, MN-major
-            // Descriptor bases are loop invariants: build them once; per UMMA only the 14-bit address field (16-byte units,
-            // low word) advances by a compile-time constant (all tiles live below 256 KiB, so no carry into the LBO field).
-            uint64_t dq[2], dk[PT_STAGES], dv[PT_STAGES], dp[2][2];
-            for (int x = 0; x < 2; x++) {
-                dq[x] = make_smem_desc(smem_u32(q_sm + x * PT_Q_BYTES), 16, 1024);
-                for (int b = 0; b < 2; b++) dp[x][b] = make_smem_desc(smem_u32(p_sm + (x * 2 + b) * PT_P_BYTES), 16, 1024);
-            }
-            for (int st = 0; st < PT_STAGES; st++) {
-                dk[st] = make_smem_desc(smem_u32(k_sm + st * PT_KV_BYTES), 16, 1024);
-                dv[st] = make_smem_desc(smem_u32(v_sm + st * PT_KV_BYTES), PT_KV_BYTES / 2, 1024);      // MN-major: LBO = d-half stride
-            }
+            constexpr uint32_t FULL = 0xffffffffu;
+            const uint32_t tm = __shfl_sync(FULL, tmem, 0);
+            // Descriptor bases are loop invariants; per UMMA only the 14-bit address field (16-byte units, low word)
+            // advances by a compile-time constant (all tiles live below 256 KiB, so no carry into the LBO field).
+            const uint64_t dq0 = make_smem_desc(smem_u32(q_sm), 16, 1024);
+            const uint64_t dk0 = make_smem_desc(smem_u32(k_sm), 16, 1024);
+            const uint64_t dv0 = make_smem_desc(smem_u32(v_sm), PT_KV_BYTES / 2, 1024);             // MN-major: LBO = d-half stride
+            const uint64_t dp0 = make_smem_desc(smem_u32(p_sm), 16, 1024);
             mbar_wait(smem_u32(&bars->q_full), 0);
-            int js = 0, jp[2] = {0, 0};
-            const int nk[2] = {nkt_a, nkt_b};
+            int js = 0, jpa = 0, jpb = 0;
             uint32_t spins = 0;
-            while (jp[0] < nkt_a || jp[1] < nkt_b) {
+            while (jpa < nkt_a || jpb < nkt_b) {
                 bool progressed = false;
                 if (js < nkt) {      // S_A(js), S_B(js)
                     const int st = js % PT_STAGES;
                     const bool ua = js < nkt_a, ub = js < nkt_b;
                     const uint32_t spar = (js & 1) ^ 1;
-                    if (mbar_test_wait(smem_u32(&bars->k_full[st]), (js / PT_STAGES) & 1) &&
-                        (!ua || mbar_test_wait(smem_u32(&bars->s_empty[0]), spar)) &&
-                        (!ub || mbar_test_wait(smem_u32(&bars->s_empty[1]), spar))) {
+                    const bool ready = mbar_test_wait(smem_u32(&bars->k_full[st]), (js / PT_STAGES) & 1) &&
+                                       (!ua || mbar_test_wait(smem_u32(&bars->s_empty[0]), spar)) &&
+                                       (!ub || mbar_test_wait(smem_u32(&bars->s_empty[1]), spar));
+                    if (__all_sync(FULL, ready)) {
                         tc_fence_after();
-                        const uint64_t kd = dk[st];
-                        for (int x = 0; x < 2; x++) {
-                            if (!(x == 0 ? ua : ub)) continue;
-                            const uint64_t qd = dq[x];
+                        if (elect_one()) {
+                            const uint64_t kd = dk0 + (uint64_t)((st * PT_KV_BYTES) >> 4);
 #pragma unroll
-                            for (int ks = 0; ks < 8; ks++) {      // 16 d per UMMA; d-half = ks / 4
-                                umma_ss(tmem + x * 64, qd + (uint64_t)(((ks >> 2) * (PT_Q_BYTES / 2) + (ks & 3) * 32) >> 4),
-                                        kd + (uint64_t)(((ks >> 2) * (PT_KV_BYTES / 2) + (ks & 3) * 32) >> 4), IDESC_S, ks > 0);
+                            for (int x = 0; x < 2; x++) {
+                                if (x == 0 ? ua : ub) {
+                                    const uint64_t qd = dq0 + (uint64_t)((x * PT_Q_BYTES) >> 4);
+#pragma unroll
+                                    for (int ks = 0; ks < 8; ks++)      // 16 d per UMMA; d-half = ks / 4
+                                        umma_ss(tm + x * 64, qd + (uint64_t)(((ks >> 2) * (PT_Q_BYTES / 2) + (ks & 3) * 32) >> 4),
+                                                kd + (uint64_t)(((ks >> 2) * (PT_KV_BYTES / 2) + (ks & 3) * 32) >> 4), IDESC_S, ks > 0);
+                                    umma_commit(smem_u32(&bars->s_full[x]));
+                                }
                             }
-                            umma_commit(smem_u32(&bars->s_full[x]));
+                            umma_commit(smem_u32(&bars->k_empty[st]));
                         }
-                        umma_commit(smem_u32(&bars->k_empty[st]));
+                        __syncwarp();
                         js++;
                         progressed = true;
                     }
                 }
-                for (int x = 0; x < 2; x++) {     // PV_X(jp[x])
-                    const int j = jp[x];
-                    if (j >= nk[x] || j >= js) continue;
-                    const int st = j % PT_STAGES;
-                    const int pb = j & 1;
-                    if (mbar_test_wait(smem_u32(&bars->p_full[x][pb]), (j >> 1) & 1) &&
-                        mbar_test_wait(smem_u32(&bars->v_full[st]), (j / PT_STAGES) & 1)) {
-                        tc_fence_after();
-                        const uint64_t vd = dv[st], pd = dp[x][pb];
 #pragma unroll
-                        for (int kt = 0; kt < 4; kt++)       // 16 tokens per UMMA
-                            umma_ss(tmem + 128 + x * 128, pd + (uint64_t)((kt * 32) >> 4), vd + (uint64_t)((kt * 2048) >> 4), IDESC_O,
-                                    (j > 0 || kt > 0) ? 1u : 0u);
-                        umma_commit(smem_u32(&bars->p_empty[x][pb]));
-                        // the V stage is free once every tile that uses it has issued its PV
-                        const int other = 1 - x;
-                        if (j >= nk[other] || jp[other] > j) umma_commit(smem_u32(&bars->v_empty[st]));
-                        jp[x]++;
-                        progressed = true;
+                for (int x = 0; x < 2; x++) {     // PV_X(jp[x])
+                    const int j = x == 0 ? jpa : jpb;
+                    const int nkx = x == 0 ? nkt_a : nkt_b;
+                    if (j < nkx && j < js) {
+                        const int st = j % PT_STAGES;
+                        const int pb = j & 1;
+                        const bool ready = mbar_test_wait(smem_u32(&bars->p_full[x][pb]), (j >> 1) & 1) &&
+                                           mbar_test_wait(smem_u32(&bars->v_full[st]), (j / PT_STAGES) & 1);
+                        if (__all_sync(FULL, ready)) {
+                            tc_fence_after();
+                            // the V stage is free once every tile that uses it has issued its PV
+                            const int jo = x == 0 ? jpb : jpa, nko = x == 0 ? nkt_b : nkt_a;
+                            const bool release_v = j >= nko || jo > j;
+                            if (elect_one()) {
+                                const uint64_t vd = dv0 + (uint64_t)((st * PT_KV_BYTES) >> 4);
+                                const uint64_t pd = dp0 + (uint64_t)(((x * 2 + pb) * PT_P_BYTES) >> 4);
+#pragma unroll
+                                for (int kt = 0; kt < 4; kt++)       // 16 tokens per UMMA
+                                    umma_ss(tm + 128 + x * 128, pd + (uint64_t)((kt * 32) >> 4), vd + (uint64_t)((kt * 2048) >> 4), IDESC_O,
+                                            (j > 0 || kt > 0) ? 1u : 0u);
+                                umma_commit(smem_u32(&bars->p_empty[x][pb]));
+                                if (release_v) umma_commit(smem_u32(&bars->v_empty[st]));
+                            }
+                            __syncwarp();
+                            if (x == 0) jpa++; else jpb++;
+                            progressed = true;
+                        }
                     }
                 }
                 if (progressed) spins = 0;
-                else if (++spins > (1u << 24)) { printf("sllm: prefill MMA watchdog (block %d,%d,%d js=%d jpA=%d jpB=%d)\n", blockIdx.x, blockIdx.y, blockIdx.z, js, jp[0], jp[1]); __trap(); }
+                else if (++spins > (1u << 24)) {
+                    if (lane == 0) printf("sllm: prefill MMA watchdog (block %d,%d,%d js=%d jpA=%d jpB=%d)\n", blockIdx.x, blockIdx.y, blockIdx.z, js, jpa, jpb);
+                    __trap();
+                }
             }
         }
     } else {

@@ -130,6 +130,15 @@ __device__ __forceinline__ float fast_exp2_tc(float x) {
     return y;
 }
 
+// One lane of a CONVERGED warp.  Issuing tcgen05.mma from `if (elect_one())` inside warp-uniform control flow lets ptxas
+// keep the descriptors in uniform registers; under a plain `if (lane == 0)` it wraps every UTCHMMA in a
+// uniformisation loop (~14 extra instructions per MMA, measured in profiles/).
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n .reg .pred p;\n elect.sync _|p, 0xffffffff;\n selp.u32 %0, 1, 0, p;\n}\n" : "=r"(pred));
+    return pred != 0;
+}
+
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
