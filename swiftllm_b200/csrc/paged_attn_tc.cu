@@ -64,7 +64,9 @@ __device__ __forceinline__ bool get_item(const TcParams& p, int idx, Item& it) {
     it.split = idx % p.num_splits;
     it.kvh = (idx / p.num_splits) % p.nkv;
     it.seq = idx / (p.num_splits * p.nkv);
-    const int len = p.seq_lens[it.seq];
+    // every caller is a converged warp: broadcasting the loaded length makes it (and everything derived from it)
+    // provably warp-uniform for the compiler
+    const int len = __shfl_sync(0xffffffffu, p.seq_lens[it.seq], 0);
     it.split_start = it.split * p.split_tokens;
     if (it.split_start >= len) return false;
     it.split_len = min(p.split_tokens, len - it.split_start);
@@ -196,10 +198,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1) paged_attn_tc_kernel(const __gr
     } else if (warp == 6) {
         producer_loop<false>(p, &vmap, &qmap, v_sm, bars->v_full, bars->v_empty, TC_VSTAGES, bars, q_sm, g, lane);
     } else if (warp == 1) {
-        // =========================================================== MMA issuer (lane 0): two in-order queues, polled
-        if (lane == 0) {
+        // =========================================================== MMA issuer: two in-order queues, polled.  The whole warp
+        // runs the loop converged (votes keep the control flow provably uniform) and one elected lane issues, so ptxas keeps
+        // the UMMA descriptors in uniform registers instead of wrapping every UTCHMMA in a uniformisation loop.
+        {
             constexpr uint32_t IDESC_S = make_instr_desc(128, TC_NPAD, UmmaFmt<T>::value, 0, 0);   // A K-major, B K-major
             constexpr uint32_t IDESC_O = make_instr_desc(128, TC_NPAD, UmmaFmt<T>::value, 1, 0);   // A MN-major (V^T)
+            constexpr uint32_t FULL = 0xffffffffu;
+            const uint32_t tm = __shfl_sync(FULL, tmem, 0);
+            const uint64_t dk0 = make_smem_desc(smem_u32(k_sm), 16, p.k_sbo);
+            const uint64_t dq0 = make_smem_desc(smem_u32(q_sm), 16, 1024);
+            const uint64_t dv0 = make_smem_desc(smem_u32(v_sm), p.v_lbo, p.v_sbo);
+            const uint64_t dp0 = make_smem_desc(smem_u32(p_sm), 16, 1024);
             TileCursor cs, cp;                  // next S tile / next PV tile
             cs.init(p); cp.init(p);
             uint32_t spins = 0;
@@ -208,21 +218,24 @@ __global__ void __launch_bounds__(TC_THREADS, 1) paged_attn_tc_kernel(const __gr
                 if (cs.valid) {
                     const uint32_t t = cs.t;
                     const int stage = t % TC_KSTAGES, b = t & 1, qb = cs.n & 1;
-                    if ((cs.j > 0 || mbar_test_wait(smem_u32(&bars->q_full[qb]), (cs.n >> 1) & 1)) &&
-                        mbar_test_wait(smem_u32(&bars->k_full[stage]), (t / TC_KSTAGES) & 1) &&
-                        mbar_test_wait(smem_u32(&bars->s_empty[b]), ((t >> 1) & 1) ^ 1)) {
+                    const bool ready = (cs.j > 0 || mbar_test_wait(smem_u32(&bars->q_full[qb]), (cs.n >> 1) & 1)) &&
+                                       mbar_test_wait(smem_u32(&bars->k_full[stage]), (t / TC_KSTAGES) & 1) &&
+                                       mbar_test_wait(smem_u32(&bars->s_empty[b]), ((t >> 1) & 1) ^ 1);
+                    if (__all_sync(FULL, ready)) {
                         tc_fence_after();
-                        const uint32_t kbase = smem_u32(k_sm + stage * TC_K_BYTES);
-                        const uint32_t qbase = smem_u32(q_sm + qb * TC_Q_BYTES);
+                        const bool last = cs.j == cs.it.ntiles - 1;
+                        if (elect_one()) {
+                            const uint64_t kd = dk0 + (uint64_t)((stage * TC_K_BYTES) >> 4);
+                            const uint64_t qd = dq0 + (uint64_t)((qb * TC_Q_BYTES) >> 4);
 #pragma unroll
-                        for (int ks = 0; ks < 8; ks++) {    // 16 d per UMMA; d-half = ks / 4
-                            const uint64_t a = make_smem_desc(kbase + (ks >> 2) * p.half_stride + (ks & 3) * 32, 16, p.k_sbo);
-                            const uint64_t bd = make_smem_desc(qbase + (ks >> 2) * 2048 + (ks & 3) * 32, 16, 1024);
-                            umma_ss(tmem + b * 16, a, bd, IDESC_S, ks > 0);
+                            for (int ks = 0; ks < 8; ks++)      // 16 d per UMMA; d-half = ks / 4
+                                umma_ss(tm + b * 16, kd + (uint64_t)(((ks >> 2) * p.half_stride + (ks & 3) * 32) >> 4),
+                                        qd + (uint64_t)(((ks >> 2) * 2048 + (ks & 3) * 32) >> 4), IDESC_S, ks > 0);
+                            umma_commit(smem_u32(&bars->s_full[b]));
+                            umma_commit(smem_u32(&bars->k_empty[stage]));                       // K tile consumed
+                            if (last) umma_commit(smem_u32(&bars->q_empty[qb]));                // Q buffer reusable
                         }
-                        umma_commit(smem_u32(&bars->s_full[b]));
-                        umma_commit(smem_u32(&bars->k_empty[stage]));                       // K tile consumed
-                        if (cs.j == cs.it.ntiles - 1) umma_commit(smem_u32(&bars->q_empty[qb]));   // Q buffer reusable
+                        __syncwarp();
                         cs.advance(p);
                         progressed = true;
                     }
@@ -230,26 +243,31 @@ __global__ void __launch_bounds__(TC_THREADS, 1) paged_attn_tc_kernel(const __gr
                 if (cp.t < cs.t || !cs.valid) {
                     const uint32_t t = cp.t;
                     const int stage = t % TC_VSTAGES, b = t & 1;
-                    if (mbar_test_wait(smem_u32(&bars->p_full[b]), (t >> 1) & 1) &&
-                        mbar_test_wait(smem_u32(&bars->v_full[stage]), (t / TC_VSTAGES) & 1) &&
-                        mbar_test_wait(smem_u32(&bars->o_empty[b]), ((t >> 1) & 1) ^ 1)) {
+                    const bool ready = mbar_test_wait(smem_u32(&bars->p_full[b]), (t >> 1) & 1) &&
+                                       mbar_test_wait(smem_u32(&bars->v_full[stage]), (t / TC_VSTAGES) & 1) &&
+                                       mbar_test_wait(smem_u32(&bars->o_empty[b]), ((t >> 1) & 1) ^ 1);
+                    if (__all_sync(FULL, ready)) {
                         tc_fence_after();
-                        const uint32_t vbase = smem_u32(v_sm + stage * TC_K_BYTES);
-                        const uint32_t pbase = smem_u32(p_sm + b * TC_P_BYTES);
+                        if (elect_one()) {
+                            const uint64_t vd = dv0 + (uint64_t)((stage * TC_K_BYTES) >> 4);
+                            const uint64_t pd = dp0 + (uint64_t)((b * TC_P_BYTES) >> 4);
 #pragma unroll
-                        for (int kt = 0; kt < 8; kt++) {        // 16 tokens (one page) per UMMA
-                            const uint64_t a = make_smem_desc(vbase + kt * p.page_stride, p.v_lbo, p.v_sbo);
-                            const uint64_t bd = make_smem_desc(pbase + (kt >> 2) * 2048 + (kt & 3) * 32, 16, 1024);
-                            umma_ss(tmem + 32 + b * 16, a, bd, IDESC_O, kt > 0);
+                            for (int kt = 0; kt < 8; kt++)      // 16 tokens (one page) per UMMA
+                                umma_ss(tm + 32 + b * 16, vd + (uint64_t)((kt * p.page_stride) >> 4),
+                                        pd + (uint64_t)(((kt >> 2) * 2048 + (kt & 3) * 32) >> 4), IDESC_O, kt > 0);
+                            umma_commit(smem_u32(&bars->o_full[b]));
+                            umma_commit(smem_u32(&bars->v_empty[stage]));
                         }
-                        umma_commit(smem_u32(&bars->o_full[b]));
-                        umma_commit(smem_u32(&bars->v_empty[stage]));
+                        __syncwarp();
                         cp.advance(p);
                         progressed = true;
                     }
                 }
                 if (progressed) spins = 0;
-                else if (++spins > (1u << 24)) { printf("sllm: MMA issuer watchdog (block %d, S tile %u, PV tile %u)\n", blockIdx.x, cs.t, cp.t); __trap(); }
+                else if (++spins > (1u << 24)) {
+                    if (lane == 0) printf("sllm: MMA issuer watchdog (block %d, S tile %u, PV tile %u)\n", blockIdx.x, cs.t, cp.t);
+                    __trap();
+                }
             }
         }
     } else {
