@@ -9,9 +9,11 @@
 namespace sllm {
 
 // ------------------------------------------------------------------ RMSNorm
-// One CTA per token row.  The (post-add) row is staged in shared memory as 16-byte vectors so the row is
-// read from HBM exactly once; each thread re-reads only the vectors it wrote itself.
-template <typename T, bool FUSED_ADD>
+// One CTA per token row.  VPT > 0: the row is exactly blockDim * VPT 16-byte vectors and every thread keeps its VPT
+// vectors in registers, with all loads issued before the first use (several independent 16-byte requests in flight per
+// thread: the kernel is latency-bound otherwise; a row is read from HBM exactly once).  VPT == 0: generic row length, the
+// (post-add) row is staged in shared memory instead.
+template <typename T, bool FUSED_ADD, int VPT>
 __global__ void __launch_bounds__(512) rmsnorm_kernel(T* __restrict__ x, T* __restrict__ residual,
                                                       const T* __restrict__ weight, float eps, int hidden) {
     extern __shared__ uint4 row_smem[];
@@ -21,21 +23,40 @@ __global__ void __launch_bounds__(512) rmsnorm_kernel(T* __restrict__ x, T* __re
     T* xr = x + t * hidden;
     T* rr = FUSED_ADD ? residual + t * hidden : nullptr;
     const int nvec = hidden >> 3;
+    constexpr int NV = VPT > 0 ? VPT : 1;
+    Vec8<T> regs[NV];
 
     float ss = 0.f;
-    for (int i = threadIdx.x; i < nvec; i += blockDim.x) {
-        Vec8<T> a = ld_vec8(xr + 8 * i);
+    if (VPT > 0) {
+        Vec8<T> rv[NV];
+#pragma unroll
+        for (int v = 0; v < NV; v++) regs[v] = ld_vec8(xr + 8 * (threadIdx.x + v * blockDim.x));
         if (FUSED_ADD) {
-            Vec8<T> b = ld_vec8(rr + 8 * i);
 #pragma unroll
-            for (int j = 0; j < 4; j++) a.v[j] = __hadd2_rn(a.v[j], b.v[j]);   // s = h(x + r): storage-dtype add
-            st_vec8(rr + 8 * i, a);
+            for (int v = 0; v < NV; v++) rv[v] = ld_vec8(rr + 8 * (threadIdx.x + v * blockDim.x));
         }
-        row_smem[i] = *reinterpret_cast<uint4*>(&a);
 #pragma unroll
-        for (int j = 0; j < 4; j++) {
-            float2 f = TT::to_f2(a.v[j]);
-            ss += f.x * f.x + f.y * f.y;
+        for (int v = 0; v < NV; v++) {
+            if (FUSED_ADD) {
+#pragma unroll
+                for (int j = 0; j < 4; j++) regs[v].v[j] = __hadd2_rn(regs[v].v[j], rv[v].v[j]);   // s = h(x + r): storage-dtype add
+                st_vec8(rr + 8 * (threadIdx.x + v * blockDim.x), regs[v]);
+            }
+#pragma unroll
+            for (int j = 0; j < 4; j++) { float2 f = TT::to_f2(regs[v].v[j]); ss += f.x * f.x + f.y * f.y; }
+        }
+    } else {
+        for (int i = threadIdx.x; i < nvec; i += blockDim.x) {
+            Vec8<T> a = ld_vec8(xr + 8 * i);
+            if (FUSED_ADD) {
+                Vec8<T> b = ld_vec8(rr + 8 * i);
+#pragma unroll
+                for (int j = 0; j < 4; j++) a.v[j] = __hadd2_rn(a.v[j], b.v[j]);
+                st_vec8(rr + 8 * i, a);
+            }
+            row_smem[i] = *reinterpret_cast<uint4*>(&a);
+#pragma unroll
+            for (int j = 0; j < 4; j++) { float2 f = TT::to_f2(a.v[j]); ss += f.x * f.x + f.y * f.y; }
         }
     }
     ss = warp_sum(ss);
@@ -46,8 +67,7 @@ __global__ void __launch_bounds__(512) rmsnorm_kernel(T* __restrict__ x, T* __re
     for (int w = 0; w < nwarps; w++) total += red[w];      // same order in every thread -> identical rstd
     const float rstd = 1.0f / sqrtf(total / (float)hidden + eps);
 
-    for (int i = threadIdx.x; i < nvec; i += blockDim.x) {
-        Vec8<T> a = *reinterpret_cast<Vec8<T>*>(&row_smem[i]);
+    auto finish = [&](const Vec8<T>& a, int i) {
         Vec8<T> w = ld_vec8(weight + 8 * i);
         Vec8<T> o;
 #pragma unroll
@@ -57,6 +77,12 @@ __global__ void __launch_bounds__(512) rmsnorm_kernel(T* __restrict__ x, T* __re
             o.v[j] = TT::from_f2(make_float2((f.x * rstd) * g.x, (f.y * rstd) * g.y));
         }
         st_vec8(xr + 8 * i, o);
+    };
+    if (VPT > 0) {
+#pragma unroll
+        for (int v = 0; v < NV; v++) finish(regs[v], threadIdx.x + v * blockDim.x);
+    } else {
+        for (int i = threadIdx.x; i < nvec; i += blockDim.x) finish(*reinterpret_cast<Vec8<T>*>(&row_smem[i]), i);
     }
 }
 
@@ -64,14 +90,24 @@ template <typename T, bool FUSED>
 static int launch_rmsnorm(void* x, void* residual, const void* weight, float eps, int64_t T_, int hidden,
                           cudaStream_t stream) {
     if (T_ == 0) return 0;
-    int nvec = hidden / 8;
+    const int nvec = hidden / 8;
+    const char* what = FUSED ? "fused_add_rmsnorm" : "rmsnorm";
+    // rows of 4 x 128 .. 4 x 256 vectors (hidden 4096 .. 8192): 4 vectors per thread, 128 .. 256 threads, no shared-memory staging
+    if (nvec % 4 == 0 && (nvec / 4) % 32 == 0 && nvec / 4 >= 64 && nvec / 4 <= 256) {
+        rmsnorm_kernel<T, FUSED, 4><<<(unsigned)T_, nvec / 4, 0, stream>>>((T*)x, (T*)residual, (const T*)weight, eps, hidden);
+        return check_launch(what);
+    }
+    if (nvec % 2 == 0 && (nvec / 2) % 32 == 0 && nvec / 2 <= 256) {
+        rmsnorm_kernel<T, FUSED, 2><<<(unsigned)T_, nvec / 2, 0, stream>>>((T*)x, (T*)residual, (const T*)weight, eps, hidden);
+        return check_launch(what);
+    }
     int threads = nvec >= 512 ? 512 : (nvec >= 256 ? 256 : ((nvec + 31) / 32) * 32);
     if (threads < 32) threads = 32;
     size_t smem = (size_t)nvec * sizeof(uint4);
     if (smem > 48 * 1024)
-        cudaFuncSetAttribute(rmsnorm_kernel<T, FUSED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    rmsnorm_kernel<T, FUSED><<<(unsigned)T_, threads, smem, stream>>>((T*)x, (T*)residual, (const T*)weight, eps, hidden);
-    return check_launch(FUSED ? "fused_add_rmsnorm" : "rmsnorm");
+        cudaFuncSetAttribute(rmsnorm_kernel<T, FUSED, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    rmsnorm_kernel<T, FUSED, 0><<<(unsigned)T_, threads, smem, stream>>>((T*)x, (T*)residual, (const T*)weight, eps, hidden);
+    return check_launch(what);
 }
 
 // ------------------------------------------------------------------ rotary embedding
@@ -104,26 +140,35 @@ __global__ void __launch_bounds__(256) rotary_kernel(T* __restrict__ q, T* __res
 }
 
 // ------------------------------------------------------------------ SiLU and mul
-// x [T, 2F] = [up | gate]; x[:, :F] = h(up * h(silu(f(gate)))).  One thread per 8 outputs.
+// x [T, 2F] = [up | gate]; x[:, :F] = h(up * h(silu(f(gate)))).  One thread per 2 x 8 outputs (4 independent 16-byte loads in flight).
 template <typename T>
 __global__ void __launch_bounds__(256) silu_and_mul_kernel(T* __restrict__ x, int64_t total_vec, int64_t F) {
     using TT = Traits<T>;
-    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= total_vec) return;
+    const int64_t idx0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 2;
+    if (idx0 >= total_vec) return;
     const int64_t vec_per_row = F >> 3;
-    const int64_t t = idx / vec_per_row, c = idx % vec_per_row;
-    T* up_p = x + t * 2 * F + 8 * c;
-    Vec8<T> up = ld_vec8(up_p);
-    Vec8<T> gate = ld_vec8_stream(up_p + F);
-    Vec8<T> o;
+    const bool two = idx0 + 1 < total_vec;
+    T* up_p[2]; Vec8<T> up[2], gate[2];
 #pragma unroll
-    for (int j = 0; j < 4; j++) {
-        float2 g = TT::to_f2(gate.v[j]);
-        g.x = g.x / (1.0f + expf(-g.x));
-        g.y = g.y / (1.0f + expf(-g.y));
-        o.v[j] = __hmul2_rn(up.v[j], TT::from_f2(g));
+    for (int u = 0; u < 2; u++) {
+        const int64_t idx = idx0 + (two ? u : 0);
+        up_p[u] = x + (idx / vec_per_row) * 2 * F + 8 * (idx % vec_per_row);
     }
-    st_vec8(up_p, o);
+#pragma unroll
+    for (int u = 0; u < 2; u++) { up[u] = ld_vec8(up_p[u]); gate[u] = ld_vec8_stream(up_p[u] + F); }
+#pragma unroll
+    for (int u = 0; u < 2; u++) {
+        if (u == 1 && !two) break;
+        Vec8<T> o;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            float2 g = TT::to_f2(gate[u].v[j]);
+            g.x = g.x / (1.0f + expf(-g.x));
+            g.y = g.y / (1.0f + expf(-g.y));
+            o.v[j] = __hmul2_rn(up[u].v[j], TT::from_f2(g));
+        }
+        st_vec8(up_p[u], o);
+    }
 }
 
 }  // namespace sllm
@@ -173,7 +218,7 @@ int sllm_silu_and_mul_inplace(void* x, int64_t num_tokens, int64_t F, sllm_dtype
     SLLM_REQUIRE(x, "silu_and_mul: null pointer");
     const int64_t total = num_tokens * (F / 8);
     const int threads = 256;
-    const unsigned blocks = (unsigned)((total + threads - 1) / threads);
+    const unsigned blocks = (unsigned)(((total + 1) / 2 + threads - 1) / threads);
     SLLM_DISPATCH_DTYPE(dtype, (silu_and_mul_kernel<T><<<blocks, threads, 0, (cudaStream_t)stream>>>((T*)x, total, F)));
     return check_launch("silu_and_mul");
 }
