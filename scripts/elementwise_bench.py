@@ -18,7 +18,14 @@ except Exception:
 g = torch.Generator(device=dev); g.manual_seed(0)
 rn = lambda *s: torch.randn(*s, device=dev, dtype=dt, generator=g)
 
+ONCE = os.environ.get("EW_ONCE", "0") == "1"      # profiling aid: one launch per kernel (ncu -c 5 captures each once)
+
+
 def timed(fn, iters=10):
+    if ONCE:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); fn(); e1.record(); torch.cuda.synchronize()
+        return e0.elapsed_time(e1)
     for _ in range(3): fn()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
