@@ -40,3 +40,49 @@ def test_llama3_8b_config_shapes():
     mc = LlamaModelConfig(LLAMA3_8B)
     assert (mc.num_layers, mc.num_q_heads, mc.num_kv_heads, mc.head_dim, mc.ffn_inter_dim) == (32, 32, 8, 128, 14336)
     assert mc.get_kvslot_size(torch.bfloat16) == 128 * 1024        # 128 KiB of KV per token
+
+
+def test_row_stride_of_contiguous_and_fused_qkv_views():
+    from swiftllm_b200 import _lib
+    import pytest
+    nq, nkv, D, T = 8, 2, 128, 5
+    qkv = torch.zeros(T, (nq + 2 * nkv) * D)
+    q = qkv[:, : nq * D].unflatten(1, (nq, D)); k = qkv[:, nq * D:(nq + nkv) * D].unflatten(1, (nkv, D))
+    assert _lib.row_stride(q) == (nq + 2 * nkv) * D and _lib.row_stride(k) == (nq + 2 * nkv) * D
+    assert _lib.row_stride(q[2:]) == (nq + 2 * nkv) * D
+    assert _lib.row_stride(torch.zeros(T, nq, D)) == nq * D
+    assert _lib.row_stride(torch.zeros(1, nq, D)) >= nq * D
+    with pytest.raises(AssertionError):
+        _lib.row_stride(torch.zeros(T, D, nq).transpose(1, 2))          # heads not contiguous within a token
+
+
+def test_fused_qkv_weight_views_share_storage():
+    """q_proj / k_proj / v_proj stay available as row views of the fused GEMM operand (weight.py:131-133 semantics)."""
+    from swiftllm_b200.worker.weight import LlamaTransformerLayerWeight, synthetic_getter
+    cfg = dict(LLAMA3_8B, num_hidden_layers=1, hidden_size=256, num_attention_heads=4, num_key_value_heads=2,
+               intermediate_size=512, vocab_size=64)
+    mc = LlamaModelConfig(cfg)
+    w = LlamaTransformerLayerWeight(0, mc, torch.float32)
+    w.load_weights(synthetic_getter(seed=1, device="cpu"), 0, 1, "cpu")
+    D = mc.head_dim
+    assert w.qkv_proj.shape == ((4 + 2 * 2) * D, 256)
+    assert w.q_proj.data_ptr() == w.qkv_proj.data_ptr() and w.q_proj.shape == (4 * D, 256)
+    assert torch.equal(torch.cat([w.q_proj, w.k_proj, w.v_proj]), w.qkv_proj)
+    assert w.up_gate_proj.shape == (2 * 512, 256)                        # [up ; gate]
+    # TP slices of the fused operand are the per-rank q | k | v rows
+    w1 = LlamaTransformerLayerWeight(0, mc, torch.float32); w1.load_weights(synthetic_getter(seed=1, device="cpu"), 1, 2, "cpu")
+    assert torch.equal(w1.q_proj, w.q_proj[2 * D:]) and torch.equal(w1.k_proj, w.k_proj[D:]) and torch.equal(w1.v_proj, w.v_proj[D:])
+    assert torch.equal(w1.o_proj, w.o_proj[:, 2 * D:]) and torch.equal(w1.down_proj, w.down_proj[:, 256:])
+    assert torch.equal(w1.up_gate_proj, torch.cat([w.up_gate_proj[256:512], w.up_gate_proj[512 + 256:]]))
+
+
+def test_bench_line_contract_helpers():
+    """bench.py helpers that run without a GPU: the workload description and the thread cap of the CPU arm."""
+    import importlib.util, os, types
+    spec = importlib.util.spec_from_file_location("bench", os.path.join(os.path.dirname(os.path.dirname(__file__)), "bench.py"))
+    bench = importlib.util.module_from_spec(spec); spec.loader.exec_module(bench)
+    args = types.SimpleNamespace(model="llama3-8b", batch=256, seqlen=4096)
+    cfg = bench.workload_config(args, bench.model_dict("llama3-8b"), 2)
+    assert cfg["global_batch"] == 256 and cfg["seq_len"] == 4096 and cfg["parallelism"] == "tp2" and "workload" in cfg
+    assert 1 <= bench.cpu_threads() <= 32
+    assert bench.METRIC == "decode_tokens_per_s" and bench.UNIT == "tokens/s"
