@@ -65,3 +65,72 @@ def test_tp_shards_plus_allreduce_equal_unsharded(world):
         p.join(timeout=60)
         assert p.exitcode == 0
     assert max(errs) < 1e-5, errs
+
+
+def _worker_model(rank, world, port, ret):
+    """The PRODUCT's LlamaModel with tp_size=world on CPU (kernel wrappers -> oracle restatements, tests/cpu_shim.py; the
+    collectives run over gloo) against the unsharded oracle model: same greedy tokens, logits within fp16 tolerance, identical
+    block tables on every rank."""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import warnings
+    import numpy as np
+    import swiftllm_b200
+    from cpu_shim import product_on_cpu
+    from oracle.model import OracleLlama, OracleWeights
+    from swiftllm_b200.worker.weight import dict_getter
+    from test_host_path_cpu import _hf_tensors
+    cfg = dict(CFG, num_hidden_layers=2, vocab_size=96)
+    w = OracleWeights.random(cfg, dtype=torch.float16, seed=12, std=0.08)
+    ok = True
+    with product_on_cpu(), warnings.catch_warnings():
+        warnings.simplefilter("ignore")                    # "peer-memory exchange unavailable ... using NCCL all-reduce"
+        ec = swiftllm_b200.EngineConfig(model_path="", use_dummy=False, block_size=16, gpu_mem_utilization=0.9, num_cpu_blocks=2,
+                                        max_seqs_in_block_table=8, max_blocks_per_seq=8, max_batch_size=8, max_tokens_in_batch=128,
+                                        dtype="float16", tp_size=world, tp_rank=rank)
+        m = swiftllm_b200.LlamaModel(ec, swiftllm_b200.LlamaModelConfig(cfg))
+        m.load_weights(dict_getter(_hf_tensors(w, cfg["intermediate_size"])))
+        m.init_kvcache_and_swap(20)
+        m.post_layer.keep_logits = True
+        assert m.comm is None                              # no peer memory on CPU: the all-reduce path
+        o = OracleLlama(cfg, w, block_size=16, num_blocks=20, num_cpu_blocks=2, max_seqs_in_block_table=8, max_blocks_per_seq=8,
+                        attn="exact", dtype=torch.float16)
+        rng = np.random.default_rng(2)
+        prompts = [rng.integers(0, 96, size=n).tolist() for n in (21, 3)]
+        sids, lens = [4, 1], [21, 3]
+        ids, dec = prompts, []
+        for stepno in range(4):
+            tm, to = m.forward(ids, sids, dec), o.forward(ids, sids, dec)
+            ref = o.last_logits.float()
+            got = m.post_layer.last_logits.float()
+            rel = float((got - ref).abs().max() / ref.abs().max())
+            top2 = ref.topk(2, dim=1).values
+            clear = ((top2[:, 0] - top2[:, 1]) > 8e-3 * ref.abs().max()).tolist()
+            ok &= rel <= 4e-3 and all(a == b for a, b, c in zip(tm, to, clear) if c)
+            n = o.gpu_block_manager.num_seq_allocated_blocks
+            ok &= bool(np.array_equal(m.gpu_block_manager.num_seq_allocated_blocks.numpy(), n))
+            for s in sids:
+                ok &= bool(np.array_equal(m.gpu_block_manager.block_table.numpy()[s, : n[s]], o.gpu_block_manager.block_table[s, : n[s]]))
+            lens = [l + 1 for l in lens]
+            ids, dec = [[t] for t in to], lens
+    gathered = [None] * world
+    dist.all_gather_object(gathered, bool(ok))
+    if rank == 0:
+        ret.put(gathered)
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2])
+def test_product_model_tensor_parallel_on_cpu(world):
+    ctx = mp.get_context("spawn")
+    ret = ctx.Queue()
+    procs = [ctx.Process(target=_worker_model, args=(r, world, 29641 + world, ret)) for r in range(world)]
+    for p in procs:
+        p.start()
+    oks = ret.get(timeout=240)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert all(oks), oks
