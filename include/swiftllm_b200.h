@@ -93,6 +93,32 @@ int sllm_prefill_attention(const void* q, const void* k, const void* v, void* o,
                            int head_dim, int64_t q_row_stride, int64_t k_row_stride, int64_t v_row_stride,
                            sllm_dtype_t dtype, sllm_stream_t stream);
 
+/* ---- Chunked ("prefix-aware") prefill - SURVEY.md §8 f-1.  NEW: the reference's forward cannot express a partial prompt
+ * (its prefill attention only sees the packed k/v of the batch: swiftllm/worker/kernels/prefill_attn.py:102-139,
+ * swiftllm/worker/layers/transformer_layer.py:86-96; its store always starts at position 0: kvcache_mgmt.py:10-48).
+ * Prefill entry i of the batch is the CHUNK of its prompt that covers positions
+ * [prefill_prefix_lens[i], prefill_prefix_lens[i] + prefill_seq_lens[i]); earlier positions are already in the cache.
+ *   sllm_store_kvcache_chunked   = sllm_store_kvcache with chunk token t written to position prefix + t;
+ *   sllm_prefill_attention_paged = causal attention of the chunk's queries (q, o [Tp, nq, D] packed) over positions
+ *       0 .. prefix + chunk - 1 read from the paged caches through rows `seq_ids` of the block table (the chunk's own
+ *       K/V must have been stored first); query t sees positions <= prefix + t.  With all prefixes 0 it computes
+ *       exactly what sllm_prefill_attention computes.  head_dim 64 / 128. */
+int sllm_store_kvcache_chunked(const void* k, const void* v, void* k_cache, void* v_cache, const int32_t* block_table,
+                               const int32_t* seq_ids, const int32_t* prefill_seq_start_locs,
+                               const int32_t* prefill_seq_lens, const int32_t* prefill_prefix_lens,
+                               const int32_t* decoding_seq_lens, int num_prefill_seqs, int num_decoding_seqs,
+                               int64_t num_prefill_tokens, int max_prefill_len, int cur_layer, int num_layers,
+                               int num_kv_heads, int block_size, int head_dim, int max_blocks_per_seq,
+                               int64_t k_row_stride, int64_t v_row_stride, sllm_dtype_t dtype, sllm_stream_t stream);
+int sllm_prefill_attention_paged(const void* q, const void* k_cache, const void* v_cache, void* o,
+                                 const int32_t* block_table, const int32_t* seq_ids,
+                                 const int32_t* prefill_seq_start_locs, const int32_t* prefill_seq_lens,
+                                 const int32_t* prefill_prefix_lens, float softmax_scale, int num_prefill_seqs,
+                                 int max_prefill_len, int64_t num_prefill_tokens, int cur_layer, int num_layers,
+                                 int num_q_heads, int num_kv_heads, int block_size, int head_dim,
+                                 int max_blocks_per_seq, int64_t num_blocks, int64_t q_row_stride, sllm_dtype_t dtype,
+                                 sllm_stream_t stream);
+
 /* ---- Block-table maintenance: swiftllm/worker/kernels/block_mgmt.py:26-46, :66-80, :106-127
  * block_table int32 [max_seqs, max_blocks_per_seq]; num_seq_allocated_blocks int32 [max_seqs];
  * is_block_free uint8/bool [num_blocks]; candidate_blocks int64 [sum(block_needed)];

@@ -110,18 +110,21 @@ def rope_tables(head_dim: int, rope_theta: float, max_position_embeddings: int, 
 # --------------------------------------------------------------------------
 def store_kvcache_inplace(k, v, k_cache, v_cache, block_table, seq_ids, prefill_seq_start_locs,
                           prefill_seq_lens, decoding_seq_lens, num_prefill_seqs, num_prefill_tokens,
-                          block_size, cur_layer):
+                          block_size, cur_layer, prefill_prefix_lens=None):
     """kvcache_mgmt.py:10-79 (+ the commented torch loop at :124-132).
     k,v [T,nkv,D]; caches [num_blocks, L, nkv, bs, D]; block_table int32 [max_seqs, max_blocks_per_seq].
-    Exact copies."""
+    Exact copies.
+    `prefill_prefix_lens` (chunked prefill; not in the reference): token t of prefill chunk i goes to
+    position prefill_prefix_lens[i] + t of its sequence (the reference always writes a prompt from position 0)."""
     seq_ids = [int(s) for s in seq_ids]
     for i in range(num_prefill_seqs):
         start = int(prefill_seq_start_locs[i])
         n = int(prefill_seq_lens[i])
+        pre = 0 if prefill_prefix_lens is None else int(prefill_prefix_lens[i])
         sid = seq_ids[i]
         for t in range(n):
-            blk = int(block_table[sid, t // block_size])
-            off = t % block_size
+            blk = int(block_table[sid, (pre + t) // block_size])
+            off = (pre + t) % block_size
             k_cache[blk, cur_layer, :, off, :] = k[start + t]
             v_cache[blk, cur_layer, :, off, :] = v[start + t]
     for j in range(len(decoding_seq_lens)):
@@ -295,6 +298,37 @@ def prefill_attention_exact(q, k, v, start_locs, seq_lens, softmax_scale, out_dt
         s = s.masked_fill(~mask, float("-inf"))
         p = torch.softmax(s, dim=-1)
         out[s0:s0 + L] = torch.einsum("hqk,hkd->hqd", p, V).transpose(0, 1)
+    return out if out_dtype is None else out.to(out_dtype)
+
+
+def prefix_prefill_attention_exact(q, k_cache, v_cache, block_table, seq_ids, start_locs, chunk_lens, prefix_lens,
+                                   softmax_scale, block_size, cur_layer, out_dtype=None, compute_dtype=torch.float64):
+    """Chunked ("prefix-aware") prefill attention - SURVEY.md §8 f-1.  The reference has no such kernel (its prefill
+    attention never reads the KV cache); the definition is the one that makes a prompt processed in
+    chunks equal to the same prompt processed at once by `prefill_attention_exact`: chunk b holds the tokens at
+    positions [prefix_lens[b], prefix_lens[b] + chunk_lens[b]) of sequence seq_ids[b]; the keys/values of ALL positions
+    below prefix + chunk are read from the paged cache (the chunk's own K/V are stored first, like decode tokens,
+    transformer_layer.py:70-71 order); query i attends to positions <= prefix + i.
+    q [Tp, nq, D] packed chunks -> [Tp, nq, D]; rows not covered by any chunk stay zero."""
+    T, nq, D = q.shape
+    nkv = k_cache.shape[2]
+    g = nq // nkv
+    cd = compute_dtype
+    out = torch.zeros((T, nq, D), dtype=cd)
+    for b in range(len(chunk_lens)):
+        s0, n, pre = int(start_locs[b]), int(chunk_lens[b]), int(prefix_lens[b])
+        if n == 0:
+            continue
+        L = pre + n
+        row = block_table[int(seq_ids[b])]
+        K = _gather_kv(k_cache, row, L, block_size, cur_layer).to(cd).repeat_interleave(g, dim=0)       # [nq, L, D]
+        V = _gather_kv(v_cache, row, L, block_size, cur_layer).to(cd).repeat_interleave(g, dim=0)
+        Q = q[s0:s0 + n].to(cd).transpose(0, 1)                                                          # [nq, n, D]
+        s = torch.einsum("hqd,hkd->hqk", Q, K) * softmax_scale
+        qpos = pre + torch.arange(n)[:, None]
+        s = s.masked_fill(torch.arange(L)[None, :] > qpos, float("-inf"))
+        p = torch.softmax(s, dim=-1)
+        out[s0:s0 + n] = torch.einsum("hqk,hkd->hqd", p, V).transpose(0, 1)
     return out if out_dtype is None else out.to(out_dtype)
 
 

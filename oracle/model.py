@@ -87,15 +87,22 @@ class OracleLlama:
 
     # model.py:252-359
     @torch.inference_mode()
-    def forward(self, input_ids_list, seq_ids_list, decoding_seq_lens_list, ignore_kvcache=False):
+    def forward(self, input_ids_list, seq_ids_list, decoding_seq_lens_list, ignore_kvcache=False,
+                prefill_prefix_lens_list=None):
+        """`prefill_prefix_lens_list` (chunked prefill; not in the reference): prefill entry i is the
+        chunk of its prompt that starts at position prefill_prefix_lens_list[i]; the earlier positions are already in
+        the KV cache.  None = the reference's contract (every prefill entry is a whole prompt)."""
         num_prefill_seqs = len(input_ids_list) - len(decoding_seq_lens_list)
         flat = list(itertools.chain(*input_ids_list))
         prefill_lens = [len(s) for s in input_ids_list[:num_prefill_seqs]]
-        seq_lengths = prefill_lens + list(decoding_seq_lens_list)
+        chunked = prefill_prefix_lens_list is not None
+        prefix = [int(x) for x in prefill_prefix_lens_list] if chunked else [0] * num_prefill_seqs
+        assert len(prefix) == num_prefill_seqs and not (chunked and ignore_kvcache)
+        seq_lengths = [p + n for p, n in zip(prefix, prefill_lens)] + list(decoding_seq_lens_list)
         B, T = len(input_ids_list), len(flat)
         Tp = T - (B - num_prefill_seqs)
         starts = list(np.cumsum([0] + prefill_lens[:-1])) if prefill_lens else []
-        positions = [p for n in prefill_lens for p in range(n)] + [l - 1 for l in decoding_seq_lens_list]
+        positions = [p0 + p for p0, n in zip(prefix, prefill_lens) for p in range(n)] + [l - 1 for l in decoding_seq_lens_list]
         if not ignore_kvcache:
             self.gpu_block_manager.allocate_blocks_for_seqs(seq_ids_list, seq_lengths)
         S, nsb = K.select_seq_block_size(self.nkv, list(decoding_seq_lens_list))
@@ -117,9 +124,15 @@ class OracleLlama:
             q, k = K.rotary_embedding(q, k, cos, sin)
             if not ignore_kvcache:
                 K.store_kvcache_inplace(k, v, self.k_cache, self.v_cache, bt, seq_ids_list, starts, prefill_lens,
-                                        decoding_seq_lens_list, num_prefill_seqs, Tp, self.block_size, li)
+                                        decoding_seq_lens_list, num_prefill_seqs, Tp, self.block_size, li,
+                                        prefill_prefix_lens=prefix if chunked else None)
             o = torch.empty((T, self.H), dtype=self.dtype)
-            if num_prefill_seqs > 0:
+            if num_prefill_seqs > 0 and chunked:
+                op = K.prefix_prefill_attention_exact(q[:Tp], self.k_cache, self.v_cache, bt, seq_ids_list[:num_prefill_seqs],
+                                                      starts, prefill_lens, prefix, scale, self.block_size, li, self.dtype,
+                                                      compute_dtype=torch.float64 if self.attn == "exact" else torch.float32)
+                o[:Tp] = op.reshape(Tp, self.H)
+            elif num_prefill_seqs > 0:
                 if self.attn == "exact":
                     op = K.prefill_attention_exact(q[:Tp], k[:Tp], v[:Tp], starts, prefill_lens, scale, self.dtype)
                 else:

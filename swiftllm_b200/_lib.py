@@ -30,6 +30,8 @@ SIGNATURES = {
     "sllm_paged_attention_workspace_bytes": (_L, [_I, _I, _I, _I, _I, _I]),
     "sllm_paged_attention": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _L, _F, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _L, _L, _I, _P]),
     "sllm_prefill_attention": (_I, [_P, _P, _P, _P, _P, _P, _F, _I, _I, _L, _I, _I, _I, _L, _L, _L, _I, _P]),
+    "sllm_store_kvcache_chunked": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _L, _I, _I, _I, _I, _I, _I, _I, _L, _L, _I, _P]),
+    "sllm_prefill_attention_paged": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _F, _I, _I, _L, _I, _I, _I, _I, _I, _I, _I, _L, _L, _I, _P]),
     "sllm_set_block_table_and_num_seq_alloc_blocks": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _P]),
     "sllm_unset_block_table_and_num_seq_alloc_blocks": (_I, [_P, _P, _P, _P, _I, _I, _P]),
     "sllm_gather_allocated_blocks_and_unset": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _P]),

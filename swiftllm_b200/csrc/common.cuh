@@ -61,6 +61,9 @@ template <typename T> __device__ __forceinline__ Vec8<T> ld_vec8_stream(const T*
     return *reinterpret_cast<Vec8<T>*>(&u);
 }
 
+// shared-memory address of a generic pointer (operand of cp.async / ldmatrix / mbarrier / TMA / UMMA descriptors)
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

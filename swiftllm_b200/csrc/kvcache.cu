@@ -10,20 +10,37 @@ namespace sllm {
 // kvcache_mgmt.py:10-48.  grid (cdiv(max_prefill_len, bs), num_prefill_seqs); one CTA moves one page worth of
 // tokens: source rows [tok][head][D] -> page [head][tok][D].  16-byte vectors, both sides coalesced per
 // D-row.  Algorithmic bytes: 4 * T * nkv * D * sizeof(T) (K and V, read + write).
-template <typename T>
+// PREFIX (chunked prefill, not in the reference): token t of chunk b lands at position prefix_lens[b] + t of its
+// sequence, so the first page of a chunk may be entered in the middle; grid.x = cdiv(max_chunk_len, bs) + 1.
+template <typename T, bool PREFIX>
 __global__ void __launch_bounds__(256) store_kv_prefill_kernel(
     const T* __restrict__ k, const T* __restrict__ v, T* __restrict__ k_cache, T* __restrict__ v_cache,
     const int32_t* __restrict__ block_table, const int32_t* __restrict__ seq_ids,
     const int32_t* __restrict__ start_locs, const int32_t* __restrict__ seq_lens, int cur_layer, int num_layers,
-    int nkv, int bs, int D, int max_blocks_per_seq, int64_t k_stride, int64_t v_stride) {
-    const int b = blockIdx.y, pb = blockIdx.x;
+    int nkv, int bs, int D, int max_blocks_per_seq, int64_t k_stride, int64_t v_stride,
+    const int32_t* __restrict__ prefix_lens) {
+    const int b = blockIdx.y;
     const int len = seq_lens[b];
-    const int tok0 = pb * bs;
-    if (tok0 >= len) return;
-    const int ntok = min(bs, len - tok0);
-    const int64_t row0 = start_locs[b] + tok0;
+    int pb = blockIdx.x;          // page of the sequence this CTA fills
+    int off0 = 0;                 // first slot of the page that is written
+    int ntok;
+    int64_t row0;                 // source row of the first token written
+    if constexpr (PREFIX) {
+        const int pre = prefix_lens[b];
+        pb += pre / bs;
+        const int lo = max(pb * bs, pre), hi = min(pb * bs + bs, pre + len);
+        if (lo >= hi) return;
+        off0 = lo - pb * bs;
+        ntok = hi - lo;
+        row0 = start_locs[b] + (lo - pre);
+    } else {
+        const int tok0 = pb * bs;
+        if (tok0 >= len) return;
+        ntok = min(bs, len - tok0);
+        row0 = start_locs[b] + tok0;
+    }
     const int64_t blk = block_table[(int64_t)seq_ids[b] * max_blocks_per_seq + pb];
-    const int64_t dst0 = (blk * num_layers + cur_layer) * (int64_t)nkv * bs * D;
+    const int64_t dst0 = (blk * num_layers + cur_layer) * (int64_t)nkv * bs * D + (int64_t)off0 * D;
     const int cpr = D >> 3;                     // 16-byte chunks per D-row
     const int items = ntok * nkv * cpr;
     for (int i = threadIdx.x; i < items; i += blockDim.x) {
@@ -217,14 +234,13 @@ __global__ void __launch_bounds__(1024) allocate_blocks_kernel(
 
 using namespace sllm;
 
-extern "C" {
-
-int sllm_store_kvcache(const void* k, const void* v, void* k_cache, void* v_cache, const int32_t* block_table,
-                       const int32_t* seq_ids, const int32_t* prefill_seq_start_locs, const int32_t* prefill_seq_lens,
-                       const int32_t* decoding_seq_lens, int num_prefill_seqs, int num_decoding_seqs,
-                       int64_t num_prefill_tokens, int max_prefill_len, int cur_layer, int num_layers, int nkv,
-                       int block_size, int head_dim, int max_blocks_per_seq, int64_t k_row_stride, int64_t v_row_stride,
-                       sllm_dtype_t dtype, sllm_stream_t stream_) {
+// prefix_lens == nullptr: the reference's contract (every prefill entry starts at position 0)
+static int store_kvcache_impl(const void* k, const void* v, void* k_cache, void* v_cache, const int32_t* block_table,
+                              const int32_t* seq_ids, const int32_t* prefill_seq_start_locs, const int32_t* prefill_seq_lens,
+                              const int32_t* prefix_lens, const int32_t* decoding_seq_lens, int num_prefill_seqs,
+                              int num_decoding_seqs, int64_t num_prefill_tokens, int max_prefill_len, int cur_layer,
+                              int num_layers, int nkv, int block_size, int head_dim, int max_blocks_per_seq,
+                              int64_t k_row_stride, int64_t v_row_stride, sllm_dtype_t dtype, sllm_stream_t stream_) {
     SLLM_REQUIRE(head_dim > 0 && head_dim % 8 == 0, "store_kvcache: head_dim (%d) must be a multiple of 8", head_dim);
     SLLM_REQUIRE(k_row_stride >= (int64_t)nkv * head_dim && v_row_stride >= (int64_t)nkv * head_dim && k_row_stride % 8 == 0 &&
                  v_row_stride % 8 == 0, "store_kvcache: bad row strides (%lld, %lld)", (long long)k_row_stride, (long long)v_row_stride);
@@ -236,11 +252,19 @@ int sllm_store_kvcache(const void* k, const void* v, void* k_cache, void* v_cach
     cudaStream_t stream = (cudaStream_t)stream_;
     if (num_prefill_seqs > 0 && max_prefill_len > 0) {
         SLLM_REQUIRE(prefill_seq_start_locs && prefill_seq_lens, "store_kvcache: null prefill metadata");
-        dim3 grid(cdiv(max_prefill_len, block_size), num_prefill_seqs);
-        SLLM_DISPATCH_DTYPE(dtype, (store_kv_prefill_kernel<T><<<grid, 256, 0, stream>>>(
-                                       (const T*)k, (const T*)v, (T*)k_cache, (T*)v_cache, block_table, seq_ids,
-                                       prefill_seq_start_locs, prefill_seq_lens, cur_layer, num_layers, nkv, block_size,
-                                       head_dim, max_blocks_per_seq, k_row_stride, v_row_stride)));
+        if (prefix_lens) {
+            dim3 grid(cdiv(max_prefill_len, block_size) + 1, num_prefill_seqs);
+            SLLM_DISPATCH_DTYPE(dtype, (store_kv_prefill_kernel<T, true><<<grid, 256, 0, stream>>>(
+                                           (const T*)k, (const T*)v, (T*)k_cache, (T*)v_cache, block_table, seq_ids,
+                                           prefill_seq_start_locs, prefill_seq_lens, cur_layer, num_layers, nkv, block_size,
+                                           head_dim, max_blocks_per_seq, k_row_stride, v_row_stride, prefix_lens)));
+        } else {
+            dim3 grid(cdiv(max_prefill_len, block_size), num_prefill_seqs);
+            SLLM_DISPATCH_DTYPE(dtype, (store_kv_prefill_kernel<T, false><<<grid, 256, 0, stream>>>(
+                                           (const T*)k, (const T*)v, (T*)k_cache, (T*)v_cache, block_table, seq_ids,
+                                           prefill_seq_start_locs, prefill_seq_lens, cur_layer, num_layers, nkv, block_size,
+                                           head_dim, max_blocks_per_seq, k_row_stride, v_row_stride, nullptr)));
+        }
         int e = check_launch("store_kvcache(prefill)");
         if (e) return e;
     }
@@ -256,6 +280,33 @@ int sllm_store_kvcache(const void* k, const void* v, void* k_cache, void* v_cach
         return check_launch("store_kvcache(decode)");
     }
     return 0;
+}
+
+extern "C" {
+
+int sllm_store_kvcache(const void* k, const void* v, void* k_cache, void* v_cache, const int32_t* block_table,
+                       const int32_t* seq_ids, const int32_t* prefill_seq_start_locs, const int32_t* prefill_seq_lens,
+                       const int32_t* decoding_seq_lens, int num_prefill_seqs, int num_decoding_seqs,
+                       int64_t num_prefill_tokens, int max_prefill_len, int cur_layer, int num_layers, int nkv,
+                       int block_size, int head_dim, int max_blocks_per_seq, int64_t k_row_stride, int64_t v_row_stride,
+                       sllm_dtype_t dtype, sllm_stream_t stream) {
+    return store_kvcache_impl(k, v, k_cache, v_cache, block_table, seq_ids, prefill_seq_start_locs, prefill_seq_lens, nullptr,
+                              decoding_seq_lens, num_prefill_seqs, num_decoding_seqs, num_prefill_tokens, max_prefill_len,
+                              cur_layer, num_layers, nkv, block_size, head_dim, max_blocks_per_seq, k_row_stride, v_row_stride,
+                              dtype, stream);
+}
+
+int sllm_store_kvcache_chunked(const void* k, const void* v, void* k_cache, void* v_cache, const int32_t* block_table,
+                               const int32_t* seq_ids, const int32_t* prefill_seq_start_locs, const int32_t* prefill_seq_lens,
+                               const int32_t* prefill_prefix_lens, const int32_t* decoding_seq_lens, int num_prefill_seqs,
+                               int num_decoding_seqs, int64_t num_prefill_tokens, int max_prefill_len, int cur_layer,
+                               int num_layers, int nkv, int block_size, int head_dim, int max_blocks_per_seq,
+                               int64_t k_row_stride, int64_t v_row_stride, sllm_dtype_t dtype, sllm_stream_t stream) {
+    SLLM_REQUIRE(num_prefill_seqs == 0 || prefill_prefix_lens, "store_kvcache_chunked: null prefill_prefix_lens");
+    return store_kvcache_impl(k, v, k_cache, v_cache, block_table, seq_ids, prefill_seq_start_locs, prefill_seq_lens,
+                              prefill_prefix_lens, decoding_seq_lens, num_prefill_seqs, num_decoding_seqs, num_prefill_tokens,
+                              max_prefill_len, cur_layer, num_layers, nkv, block_size, head_dim, max_blocks_per_seq,
+                              k_row_stride, v_row_stride, dtype, stream);
 }
 
 int sllm_set_block_table_and_num_seq_alloc_blocks(int32_t* nsab, int32_t* block_table, const int64_t* cand,

@@ -5,8 +5,6 @@
 
 namespace sllm {
 
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
 // 16-byte global->shared async copy, L2 only (streaming data).  src_bytes == 0 zero-fills.
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, int src_bytes = 16) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");

@@ -39,3 +39,8 @@ class LlamaInferState:
     # forced onto the kernel by setting this field to it.
     paged_attn_seq_block_size: int = 0
     last_token_indices: Optional[torch.Tensor] = None   # [batch_size] (post_layer.py:24-31), precomputed on the host
+    # Chunked ("prefix-aware") prefill, SURVEY.md §8 f-1: prefill entry i holds the tokens at positions
+    # [prefill_prefix_lens[i], prefill_prefix_lens[i] + prefill_seq_lens[i]) of its sequence; everything before is
+    # already in the KV cache.  None = the reference's contract (whole prompts, attention over the packed k/v).
+    prefill_prefix_lens: Optional[torch.Tensor] = None  # [num_prefill_seqs] int32
+    max_prefill_kv_len: int = 0                          # max_i(prefix_i + chunk_i); 0 when not chunked

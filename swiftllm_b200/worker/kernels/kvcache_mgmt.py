@@ -25,6 +25,19 @@ def store_kvcache(
     assert block_table.dtype == torch.int32 and infer_state.seq_ids.dtype == torch.int32
     _lib.require_device(k_cache)
     num_layers, nkv, bs, D = k_cache.shape[1:]
+    prefix = getattr(infer_state, "prefill_prefix_lens", None)
+    if prefix is not None:
+        # chunked prefill (not in the reference): chunk token t goes to position prefix + t
+        assert prefix.dtype == torch.int32 and prefix.is_contiguous() and prefix.shape[0] == infer_state.num_prefill_seqs
+        _lib.check(_lib.lib().sllm_store_kvcache_chunked(
+            k.data_ptr(), v.data_ptr(), k_cache.data_ptr(), v_cache.data_ptr(), block_table.data_ptr(),
+            infer_state.seq_ids.data_ptr(),
+            _lib.ptr(infer_state.prefill_seq_start_locs), _lib.ptr(infer_state.prefill_seq_lens), prefix.data_ptr(),
+            _lib.ptr(infer_state.decoding_seq_lens),
+            infer_state.num_prefill_seqs, infer_state.num_decoding_seqs, infer_state.num_prefill_tokens,
+            infer_state.max_prefill_len, cur_layer, num_layers, nkv, bs, D, block_table.shape[1], ks, vs,
+            _lib.dtype_tag(k.dtype), _lib.stream()), "store_kvcache_chunked")
+        return
     _lib.check(_lib.lib().sllm_store_kvcache(
         k.data_ptr(), v.data_ptr(), k_cache.data_ptr(), v_cache.data_ptr(), block_table.data_ptr(),
         infer_state.seq_ids.data_ptr(),

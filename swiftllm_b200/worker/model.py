@@ -211,10 +211,8 @@ class LlamaModel:
         input_embds += residual_buf
         return self.post_layer.forward(input_embds, infer_state)
 
-    def _stage_metadata(self, flat_ids, seq_ids_list, seq_lengths_list, prefill_lens, prefill_starts, positions,
-                        last_idx):
-        """One pinned host buffer, one async H2D copy; returns int32 device views."""
-        parts = [flat_ids, seq_ids_list, seq_lengths_list, prefill_lens, prefill_starts, positions, last_idx]
+    def _stage_metadata(self, *parts):
+        """One pinned host buffer, one async H2D copy; returns int32 device views (one per host list)."""
         host = torch.tensor(list(itertools.chain(*parts)), dtype=torch.int32).pin_memory()
         dev = host.to(self.device, non_blocking=True)
         views, off = [], 0
@@ -225,33 +223,52 @@ class LlamaModel:
 
     @torch.inference_mode()
     def forward(self, input_ids_list: list, seq_ids_list: list, decoding_seq_lens_list: list,
-                ignore_kvcache: bool = False) -> list:
+                ignore_kvcache: bool = False, prefill_prefix_lens_list: Optional[list] = None) -> list:
         """model.py:252-359.  Batch layout contract: prefill sequences first (full prompt each), then decoding
-        sequences (exactly one token each); decoding_seq_lens_list[i] includes the new token."""
-        return self.forward_async(input_ids_list, seq_ids_list, decoding_seq_lens_list, ignore_kvcache).tolist()
+        sequences (exactly one token each); decoding_seq_lens_list[i] includes the new token.
+
+        `prefill_prefix_lens_list` (addition, SURVEY.md §8 f-1: chunked / SARATHI-style prefill, which the reference's
+        forward cannot express): when given, prefill entry i is the CHUNK of its prompt that starts at position
+        prefill_prefix_lens_list[i]; positions below it were written to the KV cache by earlier calls.  The chunk's
+        K/V are stored at their positions and its queries attend to the whole prefix + chunk through the block
+        table.  The token returned for a prefill entry is sampled after the chunk's last token (meaningful for the
+        final chunk of a prompt only)."""
+        return self.forward_async(input_ids_list, seq_ids_list, decoding_seq_lens_list, ignore_kvcache,
+                                  prefill_prefix_lens_list).tolist()
 
     @torch.inference_mode()
-    def forward_async(self, input_ids_list, seq_ids_list, decoding_seq_lens_list, ignore_kvcache=False) -> torch.Tensor:
+    def forward_async(self, input_ids_list, seq_ids_list, decoding_seq_lens_list, ignore_kvcache=False,
+                      prefill_prefix_lens_list=None) -> torch.Tensor:
         """Same as forward() but returns the token tensor on the device (no sync)."""
         mc = self.model_config
         num_prefill_seqs = len(input_ids_list) - len(decoding_seq_lens_list)
         flat_ids = list(itertools.chain(*input_ids_list))
         prefill_lens = [len(s) for s in input_ids_list[:num_prefill_seqs]]
-        seq_lengths_list = prefill_lens + list(decoding_seq_lens_list)
+        chunked = prefill_prefix_lens_list is not None and num_prefill_seqs > 0
+        if chunked:
+            prefix_lens = [int(x) for x in prefill_prefix_lens_list]
+            assert len(prefix_lens) == num_prefill_seqs and min(prefix_lens) >= 0, \
+                "prefill_prefix_lens_list needs one non-negative entry per prefill sequence"
+            assert not ignore_kvcache, "chunked prefill reads the KV cache: ignore_kvcache is not applicable"
+        else:
+            prefix_lens = [0] * num_prefill_seqs
+        seq_lengths_list = [p + n for p, n in zip(prefix_lens, prefill_lens)] + list(decoding_seq_lens_list)
         batch_size, num_tokens = len(input_ids_list), len(flat_ids)
         num_prefill_tokens = num_tokens - (batch_size - num_prefill_seqs)
         prefill_starts = list(itertools.accumulate([0] + prefill_lens[:-1])) if prefill_lens else []
         max_prefill_len = max(prefill_lens) if prefill_lens else 0
         max_decoding_len = max(decoding_seq_lens_list) if decoding_seq_lens_list else 0
-        positions = [p for n in prefill_lens for p in range(n)] + [l - 1 for l in decoding_seq_lens_list]
+        positions = [p0 + p for p0, n in zip(prefix_lens, prefill_lens) for p in range(n)] + \
+            [l - 1 for l in decoding_seq_lens_list]
         last_idx = [s + n - 1 for s, n in zip(prefill_starts, prefill_lens)] + list(range(num_prefill_tokens, num_tokens))
 
         if (getattr(self.engine_config, "use_cuda_graph", False) and num_prefill_seqs == 0 and not ignore_kvcache
                 and batch_size > 0):
             return self._forward_decode_graph(flat_ids, seq_ids_list, list(decoding_seq_lens_list), max_decoding_len)
 
-        ids, seq_ids, seq_lengths, p_lens, p_starts, pos, last = self._stage_metadata(
-            flat_ids, seq_ids_list, seq_lengths_list, prefill_lens, prefill_starts, positions, last_idx)
+        ids, seq_ids, seq_lengths, p_lens, p_starts, pos, last, p_prefix = self._stage_metadata(
+            flat_ids, seq_ids_list, seq_lengths_list, prefill_lens, prefill_starts, positions, last_idx,
+            prefix_lens if chunked else [])
 
         if not ignore_kvcache:
             self.gpu_block_manager.allocate_blocks_for_seqs(seq_ids, seq_lengths, seq_ids_list=seq_ids_list,
@@ -274,6 +291,8 @@ class LlamaModel:
             position_cos=self._cos_cached.index_select(0, pos), position_sin=self._sin_cached.index_select(0, pos),
             ignore_kvcache=ignore_kvcache,
             paged_attn_seq_block_size=0, last_token_indices=last,
+            prefill_prefix_lens=p_prefix if chunked else None,
+            max_prefill_kv_len=max(seq_lengths_list[:num_prefill_seqs]) if chunked else 0,
         )
         return self._forward(ids, infer_state)
 

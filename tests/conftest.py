@@ -12,6 +12,20 @@ GOLDEN_DIR = os.path.join(ROOT, "tests", "golden")
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run with -m gpu on the B200 box)")
+    config.addinivalue_line("markers", "pending_gpu: GPU test of code that was written and cross-compiled when no GPU time was "
+                                       "left (never executed on hardware yet); skipped unless SLLM_RUN_PENDING=1")
+
+
+def pytest_collection_modifyitems(config, items):
+    """Tests of kernels that have never run on a GPU must not be able to turn the validated suite red (the driver runs
+    `-m gpu -x`).  They are opted into with SLLM_RUN_PENDING=1 (scripts/gpu_validate_pending.sh) and lose the marker once
+    they have passed on a B200."""
+    if os.environ.get("SLLM_RUN_PENDING", "") == "1":
+        return
+    skip = pytest.mark.skip(reason="pending first GPU validation: set SLLM_RUN_PENDING=1 to run")
+    for item in items:
+        if "pending_gpu" in item.keywords:
+            item.add_marker(skip)
 
 
 @pytest.fixture(scope="session")

@@ -74,6 +74,13 @@ def _prefill_attention(q, k, v, o, model_config, engine_config, st):
     o.copy_(out.reshape(o.shape))
 
 
+def _prefill_attention_paged(q, k_cache, v_cache, block_table, o, model_config, engine_config, st, cur_layer):
+    out = K.prefix_prefill_attention_exact(q, k_cache, v_cache, block_table.numpy(), st.seq_ids[:st.num_prefill_seqs].tolist(),
+                                           st.prefill_seq_start_locs.tolist(), st.prefill_seq_lens.tolist(),
+                                           st.prefill_prefix_lens.tolist(), st.softmax_scale, k_cache.shape[3], cur_layer, q.dtype)
+    o.copy_(out.reshape(o.shape))
+
+
 def _allocate_blocks(nsab, block_table, is_free, seq_ids, target_lens, block_size, new_blocks, status):
     """block_manager.py:43-79 of the reference: the lowest free ids, ascending, handed out in batch order."""
     free_ids = torch.nonzero(is_free).flatten().tolist()
@@ -117,6 +124,7 @@ _PATCHES = [
     ("swiftllm_b200.worker.layers.transformer_layer", "store_kvcache", _store_kvcache),
     ("swiftllm_b200.worker.layers.transformer_layer", "paged_attention", _paged_attention),
     ("swiftllm_b200.worker.layers.transformer_layer", "prefill_attention", _prefill_attention),
+    ("swiftllm_b200.worker.layers.transformer_layer", "prefill_attention_paged", _prefill_attention_paged),
     ("swiftllm_b200.worker.layers.post_layer", "rmsnorm_inplace", _rmsnorm_inplace),
     ("swiftllm_b200.worker.block_manager", "_allocate_kernel", _allocate_blocks),
     ("swiftllm_b200.worker.block_manager", "unset_block_table_and_num_seq_alloc_blocks", _unset),

@@ -32,6 +32,42 @@ def test_library_exports_every_declared_symbol():
     assert _lib.lib().sllm_abi_version() == 1
 
 
+def _prototypes():
+    """name -> (return type, [parameter types]) parsed from the header, reduced to the ctypes classes of _lib.py."""
+    src = open(os.path.join(ROOT, "include", "swiftllm_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    out = {}
+    for ret, name, params in re.findall(r"\b(int64_t|int|const char\*)\s+(sllm_[a-z0-9_]+)\s*\(([^)]*)\)\s*;", src):
+        kinds = []
+        for prm in [x.strip() for x in params.split(",") if x.strip() and x.strip() != "void"]:
+            if "*" in prm or prm.startswith("sllm_stream_t"):
+                kinds.append("ptr")
+            elif prm.startswith("int64_t"):
+                kinds.append("i64")
+            elif prm.startswith("float"):
+                kinds.append("f32")
+            elif prm.startswith(("int ", "sllm_dtype_t")):
+                kinds.append("i32")
+            else:
+                raise AssertionError(f"unparsed parameter {prm!r} of {name}")
+        out[name] = ({"int": "i32", "int64_t": "i64", "const char*": "str"}[ret], kinds)
+    return out
+
+
+def test_ctypes_signatures_match_the_header_type_by_type():
+    """A ctypes table that drifts from the header corrupts arguments silently (an int64 passed as int truncates, a
+    missing parameter shifts every later one): compare every prototype with _lib.SIGNATURES."""
+    from ctypes import c_char_p, c_float, c_int, c_int64, c_void_p
+    from swiftllm_b200 import _lib
+    kind = {c_void_p: "ptr", c_int: "i32", c_int64: "i64", c_float: "f32", c_char_p: "str"}
+    protos = _prototypes()
+    assert set(protos) == set(_lib.SIGNATURES)
+    for name, (ret, params) in protos.items():
+        res, args = _lib.SIGNATURES[name]
+        assert kind[res] == ret, f"{name}: return type {kind[res]} != header {ret}"
+        assert [kind[a] for a in args] == params, f"{name}: ctypes argtypes differ from the header"
+
+
 def test_invalid_arguments_are_rejected_before_launch():
     """Shape validation runs on the host and needs no GPU (the reference raises AssertionError here)."""
     from swiftllm_b200 import _lib
@@ -41,6 +77,10 @@ def test_invalid_arguments_are_rejected_before_launch():
     assert l.sllm_paged_attention(1, 1, 1, 1, 1, 1, 1, None, 0, 1.0, 1, 16, 0, 0, 1, 4, 2, 16, 96, 4, 4, 4 * 96, 0, None) != 0
     assert b"head_dim" in l.sllm_last_error()
     assert l.sllm_silu_and_mul_inplace(None, 0, 256, 7, None) == 0              # empty batch is a no-op
+    assert l.sllm_prefill_attention_paged(1, 1, 1, 1, 1, 1, 1, 1, 1, 1.0, 1, 8, 8, 0, 1, 4, 2, 16, 96, 4, 4, 4 * 96, 0, None) != 0
+    assert b"head_dim" in l.sllm_last_error()
+    assert l.sllm_store_kvcache_chunked(1, 1, 1, 1, 1, 1, 1, 1, None, None, 1, 0, 8, 8, 0, 1, 2, 16, 64, 4, 128, 128, 0, None) != 0
+    assert b"prefill_prefix_lens" in l.sllm_last_error()
     assert l.sllm_swap_blocks(None, None, 0, 1, None, None, None, None, 16, None) == 0
 
 

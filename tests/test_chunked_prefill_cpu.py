@@ -1,0 +1,120 @@
+"""CPU: chunked ("prefix-aware", SARATHI-style) prefill - SURVEY.md §8 f-1.
+
+The reference cannot express a partial prompt, so there is no reference output to pin against; the definition is
+"processing a prompt in chunks gives what processing it at once gives".  These tests hold (a) the oracle's chunked path to
+the oracle's whole-prompt path (which IS pinned against the reference's golden trace, tests/test_oracle_golden.py), and
+(b) the product's host path (positions, block allocation across chunks, metadata staging, layer dispatch) to the oracle."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import kernels as K
+from oracle.model import OracleLlama, OracleWeights
+from cpu_shim import product_on_cpu
+from test_host_path_cpu import CFG, ENG, _oracle, _product, _same_state
+
+
+def _rand_cache(rng, nb, L, nkv, bs, D, dtype):
+    return torch.from_numpy(rng.standard_normal((nb, L, nkv, bs, D)).astype(np.float32)).to(dtype)
+
+
+def test_oracle_prefix_attention_with_zero_prefix_is_plain_prefill_attention():
+    rng = np.random.default_rng(0)
+    nq, nkv, D, bs, L = 4, 2, 32, 16, 2
+    lens = [37, 16, 5]
+    starts = [0, 37, 53]
+    T = sum(lens)
+    q = torch.from_numpy(rng.standard_normal((T, nq, D)).astype(np.float32)).half()
+    k = torch.from_numpy(rng.standard_normal((T, nkv, D)).astype(np.float32)).half()
+    v = torch.from_numpy(rng.standard_normal((T, nkv, D)).astype(np.float32)).half()
+    kc, vc = _rand_cache(rng, 12, L, nkv, bs, D, torch.float16), _rand_cache(rng, 12, L, nkv, bs, D, torch.float16)
+    bt = np.full((4, 4), -1, dtype=np.int32)
+    bt[3, :3] = [7, 2, 9]; bt[0, :1] = [4]; bt[1, :1] = [11]
+    sids = [3, 0, 1]
+    K.store_kvcache_inplace(k, v, kc, vc, bt, sids, starts, lens, [], 3, T, bs, 1, prefill_prefix_lens=[0, 0, 0])
+    kc2, vc2 = kc.clone(), vc.clone()
+    K.store_kvcache_inplace(k, v, kc2, vc2, bt, sids, starts, lens, [], 3, T, bs, 1)
+    assert torch.equal(kc, kc2) and torch.equal(vc, vc2)
+    a = K.prefix_prefill_attention_exact(q, kc, vc, bt, sids, starts, lens, [0, 0, 0], D ** -0.5, bs, 1)
+    b = K.prefill_attention_exact(q, k, v, starts, lens, D ** -0.5)
+    assert float((a - b).abs().max()) < 1e-12
+
+
+def test_oracle_store_with_prefix_enters_pages_in_the_middle():
+    rng = np.random.default_rng(1)
+    nkv, D, bs, L = 2, 16, 16, 1
+    kc, vc = torch.zeros(6, L, nkv, bs, D, dtype=torch.float16), torch.zeros(6, L, nkv, bs, D, dtype=torch.float16)
+    bt = np.array([[5, 1, 3, 0]], dtype=np.int32)
+    k = torch.from_numpy(rng.standard_normal((20, nkv, D)).astype(np.float32)).half()
+    v = torch.from_numpy(rng.standard_normal((20, nkv, D)).astype(np.float32)).half()
+    K.store_kvcache_inplace(k, v, kc, vc, bt, [0], [0], [20], [], 1, 20, bs, 0, prefill_prefix_lens=[13])    # positions 13..32
+    flat_k = torch.cat([kc[b, 0] for b in (5, 1, 3)], dim=1)          # [nkv, 48, D] in sequence order
+    assert torch.equal(flat_k[:, 13:33].transpose(0, 1), k)
+    assert float(flat_k[:, :13].abs().max()) == 0 and float(flat_k[:, 33:].abs().max()) == 0
+
+
+@pytest.mark.parametrize("chunks", [(16, 16, 5), (7, 30), (1, 35, 1), (37,)])
+def test_oracle_chunked_prefill_equals_whole_prompt_prefill(chunks):
+    """Same prompt, same weights: the logits after the last chunk equal the whole-prompt logits up to the rounding of the
+    attention output (the two paths sum the same fp64 terms in a different grouping), the KV cache likewise, the sampled token
+    exactly; a decode step after either gives the same token."""
+    w = OracleWeights.random(CFG, dtype=torch.float16, seed=4, std=0.08)
+    rng = np.random.default_rng(11)
+    prompt = rng.integers(0, 300, size=sum(chunks)).tolist()
+    whole, chunked = _oracle(w), _oracle(w)
+    t_whole = whole.forward([prompt], [2], [])
+    pos = 0
+    for n in chunks:
+        t_chunk = chunked.forward([prompt[pos:pos + n]], [2], [], prefill_prefix_lens_list=[pos])
+        pos += n
+    assert t_chunk == t_whole
+    ref = whole.last_logits
+    assert float((chunked.last_logits - ref).abs().max()) <= 2e-3 * float(ref.abs().max())
+    assert np.array_equal(chunked.gpu_block_manager.block_table[2, :3], whole.gpu_block_manager.block_table[2, :3])
+    assert float((chunked.k_cache.float() - whole.k_cache.float()).abs().max()) <= 4e-3
+    assert float((chunked.v_cache.float() - whole.v_cache.float()).abs().max()) <= 4e-3
+    assert whole.forward([t_whole], [2], [len(prompt) + 1]) == chunked.forward([t_chunk], [2], [len(prompt) + 1])
+
+
+def test_product_host_path_chunked_prefill_matches_oracle_on_cpu():
+    """SARATHI-style schedule through the PRODUCT's forward on CPU (oracle-backed kernels): two prompts chunked differently,
+    a third sequence decoding in the same batches.  Tokens, logits, block tables, free map and host mirror must match the
+    oracle fed the same calls; the final tokens must equal those of whole-prompt prefill."""
+    w = OracleWeights.random(CFG, dtype=torch.float16, seed=6, std=0.08)
+    rng = np.random.default_rng(21)
+    pa, pb = rng.integers(0, 300, size=45).tolist(), rng.integers(0, 300, size=23).tolist()
+    pc = rng.integers(0, 300, size=9).tolist()
+    with product_on_cpu():
+        m, o, whole = _product(w), _oracle(w), _oracle(w)
+
+        def step(ids, sids, dlens, prefix):
+            tm = m.forward(ids, sids, dlens, prefill_prefix_lens_list=prefix)
+            to = o.forward(ids, sids, dlens, prefill_prefix_lens_list=prefix)
+            assert tm == to
+            ref = o.last_logits
+            assert float((m.post_layer.last_logits - ref).abs().max()) <= 1e-5 * float(ref.abs().max())
+            _same_state(m, o)
+            return to
+
+        t = step([pc], [4], [], None)                                        # sequence 4: ordinary whole-prompt prefill
+        lc = len(pc)
+        # batch 1: first chunks of A (seq 1) and B (seq 6) + decode of seq 4
+        lc += 1; t = step([pa[:20], pb[:16], [t[0]]], [1, 6, 4], [lc], [0, 0])
+        # batch 2: second chunk of A (enters a page in the middle), rest of B + decode
+        lc += 1; t = step([pa[20:33], pb[16:], [t[2]]], [1, 6, 4], [lc], [20, 16])
+        tb = t[1]
+        # batch 3: last chunk of A alone with the decodes of B and 4
+        lc += 1; t = step([pa[33:], [tb], [t[2]]], [1, 6, 4], [len(pb) + 1, lc], [33])
+        ta = t[0]
+        assert whole.forward([pa, pb], [1, 6], []) == [ta, tb]
+        assert m.gpu_block_manager.get_num_allocated_blocks_host([1, 6, 4]) == [3, 2, 1]
+
+
+def test_product_rejects_inconsistent_chunk_arguments():
+    w = OracleWeights.random(CFG, dtype=torch.float16, seed=3, std=0.08)
+    with product_on_cpu():
+        m = _product(w)
+        with pytest.raises(AssertionError, match="one non-negative entry per prefill"):
+            m.forward([[1, 2, 3], [4, 5]], [0, 1], [], prefill_prefix_lens_list=[0])
+        with pytest.raises(AssertionError, match="ignore_kvcache"):
+            m.forward([[1, 2, 3]], [0], [], ignore_kvcache=True, prefill_prefix_lens_list=[0])
