@@ -51,6 +51,8 @@ def parse():
                     help="TP: force the one-shot peer-memory all-reduce fused with add+RMSNorm (default: automatic, tp 2..4)")
     ap.add_argument("--nccl-allreduce", dest="fused_allreduce", action="store_false",
                     help="TP: force NCCL all-reduce + separate add/norm kernel")
+    ap.add_argument("--shard-lm-head", action="store_true",
+                    help="TP: vocabulary-sharded lm_head + (max, argmax) all-gather instead of a replicated lm_head (opt-in A/B)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-prefill", action="store_true")
     ap.add_argument("--cpu-sample-seqs", type=int, default=8)
@@ -214,7 +216,8 @@ def run_ours(args):
     ec = swiftllm_b200.EngineConfig(model_path="", use_dummy=False, block_size=bs, gpu_mem_utilization=0.97, num_cpu_blocks=0,
                                     max_seqs_in_block_table=B, max_blocks_per_seq=blocks_per_seq + 8, max_batch_size=B,
                                     max_tokens_in_batch=max(B, 16384), dtype="bfloat16", tp_size=n, tp_rank=rank,
-                                    use_cuda_graph=not args.no_graph, fused_allreduce=args.fused_allreduce)
+                                    use_cuda_graph=not args.no_graph, fused_allreduce=args.fused_allreduce,
+                                    shard_lm_head=args.shard_lm_head)
     model = swiftllm_b200.LlamaModel(ec, mc)
     model.load_weights(synthetic_getter(seed=0, std=0.02, device=dev))
     num_blocks = B * blocks_per_seq + 64
@@ -368,6 +371,7 @@ def run_ours(args):
                      "how": "CUDA events around every paged_attention launch over K eager decode steps on the launching stream"},
         "tp_exchange": None if n == 1 else ("fused peer-memory all-reduce + add + rmsnorm (one kernel)" if model.comm is not None
                                             else "ncclAllReduce + fused_add_rmsnorm"),
+        "lm_head": "vocabulary-sharded (all-gather of per-rank argmax)" if (n > 1 and args.shard_lm_head) else "replicated",
         "clocks": clk,
         "cpu_baseline": cpu,
         "prefill": prefill,

@@ -30,6 +30,10 @@ class EngineConfig:
     # TP exchange: True = one-shot peer-memory all-reduce fused with add+RMSNorm (tp_comm.py), False = NCCL all-reduce +
     # a separate kernel, None = automatic (fused for tp_size 2..4 where it was measured faster, NCCL otherwise)
     fused_allreduce: object = None
+    # TP: shard lm_head by vocabulary rows (each rank computes logits of V/tp_size tokens; the greedy token is found with one
+    # tiny all-gather of per-rank (max logit, argmax) pairs) instead of replicating the 1 GB matrix on every rank.
+    # SURVEY.md §8 f-3.  Opt-in until it has been measured on a multi-GPU box.
+    shard_lm_head: bool = False
 
     @staticmethod
     def add_cli_args(parser: argparse.ArgumentParser):

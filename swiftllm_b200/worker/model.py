@@ -110,7 +110,8 @@ class LlamaModel:
             self.tp_group = dist.group.WORLD
         self.weight = load_weights(self.model_config, self.dtype, self.engine_config.model_path,
                                    self.engine_config.use_dummy, getter=weight_getter,
-                                   tp_rank=self.tp_rank, tp_size=self.tp_size, device=self.device)
+                                   tp_rank=self.tp_rank, tp_size=self.tp_size, device=self.device,
+                                   shard_lm_head=bool(getattr(self.engine_config, "shard_lm_head", False)))
         cos, sin = build_rope_tables(self.model_config, self.dtype)
         self._cos_cached, self._sin_cached = cos.to(self.device), sin.to(self.device)
 
@@ -141,7 +142,8 @@ class LlamaModel:
                                   decoding_piggyback_stream, i, tp_group=self.tp_group, comm=self.comm)
             for i in range(self.model_config.num_layers)
         ]
-        self.post_layer = LlamaPostLayer(self.model_config, self.weight)
+        self.post_layer = LlamaPostLayer(self.model_config, self.weight, tp_group=self.tp_group, tp_rank=self.tp_rank,
+                                         tp_size=self.tp_size)
 
     def _kvslot_bytes(self) -> int:
         return self.model_config.get_kvslot_size(self.dtype) // self.tp_size

@@ -7,7 +7,7 @@ sliced for tensor parallelism at load time:
                         k_proj / v_proj rows of kv heads [r*nkv/N, ...)     (column-parallel)
                         up / gate rows [r*F/N, (r+1)*F/N), re-fused as [up_r ; gate_r]
                         o_proj / down_proj input columns of the same slices (row-parallel, all-reduced)
-    norms, embedding and lm_head are replicated.
+    norms and the embedding are replicated; lm_head is replicated, or (shard_lm_head) split by vocabulary rows.
 """
 from __future__ import annotations
 
@@ -76,14 +76,20 @@ class LlamaWeight:
         self.model_version = model_version
         self.layers = [LlamaTransformerLayerWeight(i, model_config, dtype) for i in range(model_config.num_layers)]
 
-    def load_weights(self, getter: Callable, tp_rank: int = 0, tp_size: int = 1, device="cuda"):
+    def load_weights(self, getter: Callable, tp_rank: int = 0, tp_size: int = 1, device="cuda", shard_lm_head: bool = False):
         c = self.model_config
         vs = (c.vocab_size, c.hidden_size)
         self.wte = getter("model.embed_tokens.weight", vs, self.dtype).to(device=device, dtype=self.dtype)
-        if self.model_version == "llama3.2":      # tied embeddings (weight.py:157-163)
-            self.lm_head = self.wte
+        self.lm_head_sharded = bool(shard_lm_head) and tp_size > 1
+        if self.lm_head_sharded:
+            assert c.vocab_size % tp_size == 0, f"shard_lm_head: vocab_size {c.vocab_size} not divisible by tp_size {tp_size}"
+        if self.model_version == "llama3.2":      # tied embeddings (weight.py:157-163); a row slice of wte is a view
+            self.lm_head = tp_slice(self.wte, 0, tp_rank, tp_size) if self.lm_head_sharded else self.wte
         else:
-            self.lm_head = getter("lm_head.weight", vs, self.dtype).to(device=device, dtype=self.dtype)
+            lm_head = getter("lm_head.weight", vs, self.dtype)
+            if self.lm_head_sharded:
+                lm_head = tp_slice(lm_head, 0, tp_rank, tp_size)
+            self.lm_head = lm_head.to(device=device, dtype=self.dtype).contiguous()
         self.final_norm = getter("model.norm.weight", (c.hidden_size,), self.dtype).to(device=device, dtype=self.dtype)
         for layer in self.layers:
             layer.load_weights(getter, tp_rank, tp_size, device)
@@ -161,11 +167,11 @@ def detect_model_version(model_path: Optional[str], model_config: LlamaModelConf
 
 def load_weights(model_config: LlamaModelConfig, dtype: torch.dtype, model_path: Optional[str], use_dummy: bool = False,
                  model_version: str = "auto", getter: Optional[Callable] = None, tp_rank: int = 0, tp_size: int = 1,
-                 device="cuda") -> LlamaWeight:
+                 device="cuda", shard_lm_head: bool = False) -> LlamaWeight:
     if model_version == "auto":
         model_version = detect_model_version(model_path, model_config)
     if getter is None:
         getter = dummy_getter(device) if use_dummy else checkpoint_getter(model_path, device)
     weight = LlamaWeight(model_config, dtype, model_version)
-    weight.load_weights(getter, tp_rank, tp_size, device)
+    weight.load_weights(getter, tp_rank, tp_size, device, shard_lm_head=shard_lm_head)
     return weight

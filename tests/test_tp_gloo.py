@@ -67,7 +67,7 @@ def test_tp_shards_plus_allreduce_equal_unsharded(world):
     assert max(errs) < 1e-5, errs
 
 
-def _worker_model(rank, world, port, ret):
+def _worker_model(rank, world, port, ret, shard_lm_head=False):
     """The PRODUCT's LlamaModel with tp_size=world on CPU (kernel wrappers -> oracle restatements, tests/cpu_shim.py; the
     collectives run over gloo) against the unsharded oracle model: same greedy tokens, logits within fp16 tolerance, identical
     block tables on every rank."""
@@ -89,9 +89,10 @@ def _worker_model(rank, world, port, ret):
         warnings.simplefilter("ignore")                    # "peer-memory exchange unavailable ... using NCCL all-reduce"
         ec = swiftllm_b200.EngineConfig(model_path="", use_dummy=False, block_size=16, gpu_mem_utilization=0.9, num_cpu_blocks=2,
                                         max_seqs_in_block_table=8, max_blocks_per_seq=8, max_batch_size=8, max_tokens_in_batch=128,
-                                        dtype="float16", tp_size=world, tp_rank=rank)
+                                        dtype="float16", tp_size=world, tp_rank=rank, shard_lm_head=shard_lm_head)
         m = swiftllm_b200.LlamaModel(ec, swiftllm_b200.LlamaModelConfig(cfg))
         m.load_weights(dict_getter(_hf_tensors(w, cfg["intermediate_size"])))
+        assert m.weight.lm_head.shape[0] == (cfg["vocab_size"] // world if shard_lm_head else cfg["vocab_size"])
         m.init_kvcache_and_swap(20)
         m.post_layer.keep_logits = True
         assert m.comm is None                              # no peer memory on CPU: the all-reduce path
@@ -122,11 +123,15 @@ def _worker_model(rank, world, port, ret):
     dist.destroy_process_group()
 
 
+@pytest.mark.parametrize("shard_lm_head", [False, True], ids=["replicated-lm_head", "vocab-sharded-lm_head"])
 @pytest.mark.parametrize("world", [2])
-def test_product_model_tensor_parallel_on_cpu(world):
+def test_product_model_tensor_parallel_on_cpu(world, shard_lm_head):
+    """shard_lm_head: every rank computes V / world logit columns; the greedy token comes from one all-gather of
+    (max logit, index) pairs and must equal the unsharded argmax wherever the top-1 margin is clear."""
     ctx = mp.get_context("spawn")
     ret = ctx.Queue()
-    procs = [ctx.Process(target=_worker_model, args=(r, world, 29641 + world, ret)) for r in range(world)]
+    port = 29641 + world + (20 if shard_lm_head else 0)
+    procs = [ctx.Process(target=_worker_model, args=(r, world, port, ret, shard_lm_head)) for r in range(world)]
     for p in procs:
         p.start()
     oks = ret.get(timeout=240)
@@ -134,3 +139,18 @@ def test_product_model_tensor_parallel_on_cpu(world):
         p.join(timeout=60)
         assert p.exitcode == 0
     assert all(oks), oks
+
+
+def test_sharded_argmax_merge_prefers_the_first_occurrence():
+    """Ties at the maximum (likely with fp16 logits over a 128k vocabulary) must resolve to the smallest token id, like
+    torch.argmax over the unsharded logits does."""
+    from swiftllm_b200.worker.layers.post_layer import merge_sharded_argmax
+    g = torch.Generator().manual_seed(0)
+    N, B, Vs = 4, 9, 6
+    for _ in range(50):
+        logits = torch.randint(0, 3, (B, N * Vs), generator=g).to(torch.float16)         # lots of ties
+        shards = logits.view(B, N, Vs).permute(1, 0, 2)                                   # [N, B, Vs]
+        first = lambda row: int((row == row.max()).nonzero()[0])
+        loc = torch.tensor([[first(shards[n, b]) for b in range(B)] for n in range(N)])
+        pairs = torch.stack((shards.gather(2, loc[..., None]).squeeze(2).float(), (loc + torch.arange(N)[:, None] * Vs).float()), dim=2)
+        assert merge_sharded_argmax(pairs).tolist() == [first(logits[b]) for b in range(B)]

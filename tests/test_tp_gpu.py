@@ -25,7 +25,8 @@ def _run(rank, world, port, q):
     def make(tp, r, graph=False, fused=False):
         ec = swiftllm_b200.EngineConfig(model_path="", use_dummy=False, block_size=16, gpu_mem_utilization=0.9, num_cpu_blocks=2,
                                         max_seqs_in_block_table=8, max_blocks_per_seq=16, max_batch_size=4, max_tokens_in_batch=256,
-                                        dtype="bfloat16", tp_size=tp, tp_rank=r, use_cuda_graph=graph, fused_allreduce=fused)
+                                        dtype="bfloat16", tp_size=tp, tp_rank=r, use_cuda_graph=graph, fused_allreduce=fused,
+                                        shard_lm_head=os.environ.get("SLLM_TEST_SHARD_LM_HEAD", "0") == "1")
         m = swiftllm_b200.LlamaModel(ec, swiftllm_b200.LlamaModelConfig(CFG))
         m.load_weights(synthetic_getter(seed=11, std=0.05, device=f"cuda:{rank}"))
         m.init_kvcache_and_swap(40)
@@ -86,6 +87,30 @@ def test_tp_matches_single_gpu(world, fused, monkeypatch):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     procs = [ctx.Process(target=_run, args=(r, world, 29650 + world + (10 if fused else 0), q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    worst = q.get(timeout=300)
+    for p in procs:
+        p.join(timeout=60)
+        if p.exitcode is None:
+            p.kill()
+        assert p.exitcode == 0
+    assert worst <= 2 ** -5
+
+
+@pytest.mark.pending_gpu
+@pytest.mark.parametrize("world", [2, 4])
+def test_tp_vocab_sharded_lm_head_matches_single_gpu(world, monkeypatch):
+    """shard_lm_head=True (V / world logit columns per rank + one all-gather of (max, argmax) pairs, also inside the CUDA graph)
+    against the TP=1 model: same checks as above.  PENDING first GPU run (CPU/gloo version: tests/test_tp_gloo.py)."""
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs")
+    monkeypatch.setenv("SLLM_TEST_FUSED_AR", "0")
+    monkeypatch.setenv("SLLM_TEST_SHARD_LM_HEAD", "1")
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_run, args=(r, world, 29690 + world, q)) for r in range(world)]
     for p in procs:
         p.start()
     worst = q.get(timeout=300)
