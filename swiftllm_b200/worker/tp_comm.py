@@ -20,22 +20,34 @@ NUM_SLOTS = 2
 
 
 class FusedAllReduce:
-    def __init__(self, max_tokens: int, hidden: int, dtype: torch.dtype, device, group=None):
+    """`two_shot=False`: every rank reduces every row itself (one barrier; (N-1)*T*H remote bytes per rank; measured best for
+    TP 2..4).  `two_shot=True`: row t is reduced, added to the residual and normalised by rank t % N only, which then pushes
+    the normalised row to every rank (two barriers; 2*(N-1)/N*T*H remote bytes per rank) - meant for TP 8.  In that mode the
+    residual is only kept up to date for the rows a rank owns and `reduce_add_norm` returns a view of a symmetric buffer that
+    is overwritten by the next exchange."""
+
+    def __init__(self, max_tokens: int, hidden: int, dtype: torch.dtype, device, group=None, two_shot: bool = False):
         import torch.distributed._symmetric_memory as symm_mem
         group = group if group is not None else dist.group.WORLD
         self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
         assert 2 <= self.world <= 8
         self.max_tokens, self.hidden, self.dtype, self.device = max_tokens, hidden, dtype, device
+        self.two_shot = bool(two_shot)
         self.data = symm_mem.empty((NUM_SLOTS, max_tokens, hidden), dtype=dtype, device=device)
         self.flags = symm_mem.empty((16 * 8,), dtype=torch.int32, device=device)
         self.data.zero_(); self.flags.zero_()
         self._hd = symm_mem.rendezvous(self.data, group)
         self._hf = symm_mem.rendezvous(self.flags, group)
+        if self.two_shot:
+            self.xout = symm_mem.empty((max_tokens, hidden), dtype=dtype, device=device)
+            self.xout.zero_()
+            self._hx = symm_mem.rendezvous(self.xout, group)
         torch.cuda.synchronize(); dist.barrier(group)                  # every rank's flags are zero before first use
         slot_bytes = max_tokens * hidden * self.data.element_size()
         PtrArr = ctypes.c_void_p * self.world
         self._buf_ptrs = [PtrArr(*[int(p) + s * slot_bytes for p in self._hd.buffer_ptrs]) for s in range(NUM_SLOTS)]
         self._flag_ptrs = PtrArr(*[int(p) for p in self._hf.buffer_ptrs])
+        self._xout_ptrs = PtrArr(*[int(p) for p in self._hx.buffer_ptrs]) if self.two_shot else None
         self.epoch = torch.zeros((32,), dtype=torch.int32, device=device)
 
     def partial_out(self, slot: int, num_tokens: int) -> torch.Tensor:
@@ -46,6 +58,14 @@ class FusedAllReduce:
     def reduce_add_norm(self, slot: int, num_tokens: int, residual: torch.Tensor, weight: torch.Tensor, eps: float) -> torch.Tensor:
         """residual <- h(sum_ranks partial[slot]) + residual;  returns rmsnorm(residual) * weight (new tensor)."""
         assert residual.is_contiguous() and residual.shape == (num_tokens, self.hidden)
+        if self.two_shot:
+            assert weight is not None and num_tokens <= self.max_tokens
+            _lib.check(_lib.lib().sllm_allreduce_add_rmsnorm_2shot(
+                ctypes.cast(self._buf_ptrs[slot], ctypes.c_void_p), ctypes.cast(self._xout_ptrs, ctypes.c_void_p),
+                ctypes.cast(self._flag_ptrs, ctypes.c_void_p), self.rank, self.world, slot, self.epoch.data_ptr(),
+                residual.data_ptr(), weight.data_ptr(), eps, num_tokens, self.hidden, _lib.dtype_tag(self.dtype),
+                _lib.stream()), "allreduce_add_rmsnorm_2shot")
+            return self.xout[:num_tokens]
         out = torch.empty_like(residual)
         _lib.check(_lib.lib().sllm_allreduce_add_rmsnorm(
             ctypes.cast(self._buf_ptrs[slot], ctypes.c_void_p), ctypes.cast(self._flag_ptrs, ctypes.c_void_p),

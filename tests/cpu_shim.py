@@ -117,6 +117,45 @@ def _swap_blocks(src_ids, dst_ids, is_swap_in, k_cache, v_cache, k_swap, v_swap)
     K.swap_blocks_inplace(src_ids, dst_ids, is_swap_in, k_cache, v_cache, k_swap, v_swap)
 
 
+class GlooFusedAllReduce:
+    """CPU stand-in of swiftllm_b200.worker.tp_comm.FusedAllReduce with the SAME observable semantics as the CUDA kernels
+    (csrc/allreduce_norm.cu), exchanged over gloo: partials are summed in rank order in fp32, residual <- h(h(sum) + residual),
+    output = rmsnorm(residual) * weight.  two_shot: only the rows a rank owns (t % world == rank) are reduced / added /
+    normalised by it; its other residual rows are POISONED with NaN (the kernel simply does not maintain them), and the
+    normalised rows are gathered from their owners."""
+
+    def __init__(self, max_tokens, hidden, dtype, device, group=None, two_shot=False):
+        import torch.distributed as dist
+        self.group = group if group is not None else dist.group.WORLD
+        self.rank, self.world = dist.get_rank(self.group), dist.get_world_size(self.group)
+        self.two_shot, self.hidden, self.max_tokens = bool(two_shot), hidden, max_tokens
+        self.data = torch.zeros((2, max_tokens, hidden), dtype=dtype)
+
+    def partial_out(self, slot, num_tokens):
+        return self.data[slot, :num_tokens]
+
+    def reduce_add_norm(self, slot, num_tokens, residual, weight, eps):
+        import torch.distributed as dist
+        mine = self.data[slot, :num_tokens].contiguous()
+        parts = [torch.empty_like(mine) for _ in range(self.world)]
+        dist.all_gather(parts, mine, group=self.group)
+        acc = torch.zeros(mine.shape, dtype=torch.float32)
+        for prt in parts:                                  # fixed rank order, fp32 accumulation
+            acc += prt.float()
+        s = acc.to(mine.dtype) + residual                  # h(h(sum) + r)
+        if not self.two_shot:
+            residual.copy_(s)
+            return K.rmsnorm(s, weight, eps)
+        own = (torch.arange(num_tokens) % self.world) == self.rank
+        residual[own] = s[own]
+        residual[~own] = float("nan")
+        out = torch.zeros_like(s)
+        if bool(own.any()):
+            out[own] = K.rmsnorm(residual[own], weight, eps)
+        dist.all_reduce(out, group=self.group)             # every row has exactly one non-zero contributor: exact
+        return out
+
+
 _PATCHES = [
     ("swiftllm_b200.worker.layers.transformer_layer", "fused_add_rmsnorm_inplace", _fused_add_rmsnorm_inplace),
     ("swiftllm_b200.worker.layers.transformer_layer", "rotary_embedding_inplace", _rotary_embedding_inplace),

@@ -67,7 +67,7 @@ def test_tp_shards_plus_allreduce_equal_unsharded(world):
     assert max(errs) < 1e-5, errs
 
 
-def _worker_model(rank, world, port, ret, shard_lm_head=False):
+def _worker_model(rank, world, port, ret, shard_lm_head=False, comm=None):
     """The PRODUCT's LlamaModel with tp_size=world on CPU (kernel wrappers -> oracle restatements, tests/cpu_shim.py; the
     collectives run over gloo) against the unsharded oracle model: same greedy tokens, logits within fp16 tolerance, identical
     block tables on every rank."""
@@ -78,24 +78,27 @@ def _worker_model(rank, world, port, ret, shard_lm_head=False):
     import warnings
     import numpy as np
     import swiftllm_b200
-    from cpu_shim import product_on_cpu
+    from cpu_shim import product_on_cpu, GlooFusedAllReduce
     from oracle.model import OracleLlama, OracleWeights
     from swiftllm_b200.worker.weight import dict_getter
     from test_host_path_cpu import _hf_tensors
     cfg = dict(CFG, num_hidden_layers=2, vocab_size=96)
     w = OracleWeights.random(cfg, dtype=torch.float16, seed=12, std=0.08)
     ok = True
-    with product_on_cpu(), warnings.catch_warnings():
+    extra = [("swiftllm_b200.worker.tp_comm", "FusedAllReduce", GlooFusedAllReduce)] if comm else []
+    with product_on_cpu(extra), warnings.catch_warnings():
         warnings.simplefilter("ignore")                    # "peer-memory exchange unavailable ... using NCCL all-reduce"
         ec = swiftllm_b200.EngineConfig(model_path="", use_dummy=False, block_size=16, gpu_mem_utilization=0.9, num_cpu_blocks=2,
                                         max_seqs_in_block_table=8, max_blocks_per_seq=8, max_batch_size=8, max_tokens_in_batch=128,
-                                        dtype="float16", tp_size=world, tp_rank=rank, shard_lm_head=shard_lm_head)
+                                        dtype="float16", tp_size=world, tp_rank=rank, shard_lm_head=shard_lm_head,
+                                        fused_allreduce={None: False, "one_shot": True, "two_shot": "two_shot"}[comm])
         m = swiftllm_b200.LlamaModel(ec, swiftllm_b200.LlamaModelConfig(cfg))
         m.load_weights(dict_getter(_hf_tensors(w, cfg["intermediate_size"])))
         assert m.weight.lm_head.shape[0] == (cfg["vocab_size"] // world if shard_lm_head else cfg["vocab_size"])
         m.init_kvcache_and_swap(20)
         m.post_layer.keep_logits = True
-        assert m.comm is None                              # no peer memory on CPU: the all-reduce path
+        assert (m.comm is None) == (comm is None)          # no peer memory on CPU: the all-reduce path unless a stand-in is given
+        assert comm is None or m.comm.two_shot == (comm == "two_shot")
         o = OracleLlama(cfg, w, block_size=16, num_blocks=20, num_cpu_blocks=2, max_seqs_in_block_table=8, max_blocks_per_seq=8,
                         attn="exact", dtype=torch.float16)
         rng = np.random.default_rng(2)
@@ -154,3 +157,30 @@ def test_sharded_argmax_merge_prefers_the_first_occurrence():
         loc = torch.tensor([[first(shards[n, b]) for b in range(B)] for n in range(N)])
         pairs = torch.stack((shards.gather(2, loc[..., None]).squeeze(2).float(), (loc + torch.arange(N)[:, None] * Vs).float()), dim=2)
         assert merge_sharded_argmax(pairs).tolist() == [first(logits[b]) for b in range(B)]
+
+
+@pytest.mark.parametrize("comm", ["one_shot", "two_shot"])
+@pytest.mark.parametrize("world", [2, 3])
+def test_product_model_fused_exchange_host_path_on_cpu(world, comm):
+    """The host side of the fused exchange (GEMM partials written into the comm buffer, layer i's down_proj exchange folded
+    into layer i+1's first norm, final norm in the model tail, and - two_shot - a residual that is only maintained for the rows
+    a rank owns) with a gloo stand-in that follows the CUDA kernels' semantics (tests/cpu_shim.py: GlooFusedAllReduce; rows a
+    rank does not own are poisoned with NaN there).  world 3 leaves T = 2 tokens without an owner on one rank."""
+    ctx = mp.get_context("spawn")
+    ret = ctx.Queue()
+    port = 29700 + world + (10 if comm == "two_shot" else 0)
+    procs = [ctx.Process(target=_worker_model_w, args=(r, world, port, ret, comm)) for r in range(world)]
+    for p in procs:
+        p.start()
+    oks = ret.get(timeout=240)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert all(oks), oks
+
+
+def _worker_model_w(rank, world, port, ret, comm):
+    global CFG
+    if world == 3:                                         # heads / FFN columns must divide by the world size
+        CFG = dict(CFG, num_attention_heads=6, num_key_value_heads=3, hidden_size=96, intermediate_size=192)
+    _worker_model(rank, world, port, ret, False, comm)
