@@ -1,14 +1,15 @@
-"""Times the UNMODIFIED reference (swiftLLM, installed into baseline/_ref by pip --target; git-ignored) on the GPU:
+"""Times the UNMODIFIED reference (swiftLLM, placed under baseline/_ref/src by scripts/install_reference.sh; git-ignored) on the GPU:
 its own Triton kernels + cuBLAS, fp16 as shipped, BASELINE config 2 (Llama-3-8B shapes, pure decode, batch 256,
 seq_len 4096).  Informational companion to bench.py (the contract's `--impl reference` arm is the CPU port):
 prints one JSON line with the reference's decode step time and the time of its paged_attention (phase 1 + 2)."""
 import json, os, statistics, sys, tempfile, types
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-REF = os.path.join(ROOT, "baseline", "_ref")
-if not os.path.isdir(os.path.join(REF, "swiftllm")):
-    print(json.dumps({"impl": "reference-triton", "unavailable": "baseline/_ref/swiftllm not installed"})); sys.exit(0)
+REF = os.path.join(ROOT, "baseline", "_ref", "src")
+if not os.path.isdir(os.path.join(REF, "swiftllm", "worker")):
+    print(json.dumps({"impl": "reference-triton", "unavailable": "baseline/_ref/src missing: run scripts/install_reference.sh"})); sys.exit(0)
 sys.path.insert(0, REF)
+sys.path.insert(0, os.path.join(REF, "csrc"))          # swiftllm_c built in place (the reference's `pip install -e csrc`)
 import torch
 ray = types.ModuleType("ray"); ray.remote = lambda cls: cls; sys.modules["ray"] = ray
 try:
