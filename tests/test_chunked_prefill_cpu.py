@@ -118,3 +118,45 @@ def test_product_rejects_inconsistent_chunk_arguments():
             m.forward([[1, 2, 3], [4, 5]], [0, 1], [], prefill_prefix_lens_list=[0])
         with pytest.raises(AssertionError, match="ignore_kvcache"):
             m.forward([[1, 2, 3]], [0], [], ignore_kvcache=True, prefill_prefix_lens_list=[0])
+
+
+def test_chunked_replay_of_the_reference_golden_trace(golden):
+    """Pins the chunked path against the UNMODIFIED reference's own outputs (tests/golden/model_tiny.npz): every prefill of the
+    recorded trace is replayed in chunks (sizes that enter pages in the middle); the greedy tokens of every call must equal the
+    reference's and the logits stay within the tolerance the whole-prompt oracle is held to plus the attention-output rounding
+    (physical block ids differ by construction - chunks allocate later - so block tables are not compared here)."""
+    import json
+    z = golden("model_tiny")
+    cfg = json.loads(str(z["config"])); eng = json.loads(str(z["engine"]))
+    w = OracleWeights.from_golden(z, cfg["num_hidden_layers"])
+    m = OracleLlama(cfg, w, block_size=eng["block_size"], num_blocks=eng["num_blocks"], num_cpu_blocks=eng["num_cpu_blocks"],
+                    max_seqs_in_block_table=eng["max_seqs_in_block_table"], max_blocks_per_seq=eng["max_blocks_per_seq"])
+    calls = json.loads(str(z["calls"]))
+    checked = 0
+    for i, c in enumerate(calls):
+        if c["op"] == "forward":
+            nd = len(c["dec_lens"])
+            prompts = c["input_ids"][: len(c["input_ids"]) - nd]
+            psids = c["seq_ids"][: len(prompts)]
+            ref_tok = z[f"t{i}_tokens"].tolist()
+            ref_logits = torch.from_numpy(z[f"t{i}_logits"]).float()
+            tol = 2e-3 * float(ref_logits.abs().max())
+            # all but the last chunk of every prompt first (7-token chunks), one prompt per call
+            for p, s in zip(prompts, psids):
+                for pos in range(0, max(len(p) - 7, 0), 7):
+                    if pos + 7 < len(p):
+                        m.forward([p[pos:pos + 7]], [s], [], prefill_prefix_lens_list=[pos])
+            # then the reference's call with every prompt replaced by its last chunk (decodes piggybacked as recorded)
+            last_start = [((len(p) - 1) // 7) * 7 if len(p) > 7 else 0 for p in prompts]
+            ids = [p[a:] for p, a in zip(prompts, last_start)] + c["input_ids"][len(prompts):]
+            toks = m.forward(ids, c["seq_ids"], c["dec_lens"], prefill_prefix_lens_list=last_start if prompts else None)
+            assert toks == ref_tok, (i, toks, ref_tok)
+            assert float((m.last_logits.float() - ref_logits).abs().max()) <= tol
+            checked += 1
+        elif c["op"] == "swap_out":
+            m.swap_out_seqs(c["seq_ids"])
+        elif c["op"] == "swap_in":
+            m.swap_in_seqs(c["seq_ids"])
+        else:
+            m.free_seqs_resources(c["seq_ids"])
+    assert checked == 6

@@ -221,3 +221,41 @@ def test_model_chunked_prefill_matches_whole_prompt_and_oracle(dtype, prefill_ge
     whole = OracleLlama(CFG, w, block_size=16, num_blocks=96, num_cpu_blocks=2, max_seqs_in_block_table=8, max_blocks_per_seq=48,
                         attn="exact", dtype=tdt)
     assert whole.forward([pa, pb], [1, 6], []) == [to[0], tb]
+
+
+def test_model_chunked_replay_of_the_reference_golden_trace(golden):
+    """The recorded trace of the UNMODIFIED reference (tests/golden/model_tiny.npz, fp16, head_dim 64 -> the mma.sync paged
+    prefill kernel) replayed with every prefill issued in 7-token chunks: greedy tokens equal the reference's wherever its top-1
+    margin is clear, logits within the tolerance of the whole-prompt GPU test (tests/test_model_gpu.py)."""
+    import json
+    from test_model_gpu import _make_model
+    z = golden("model_tiny")
+    cfg = json.loads(str(z["config"])); eng = json.loads(str(z["engine"]))
+    w = OracleWeights.from_golden(z, cfg["num_hidden_layers"])
+    m = _make_model(cfg, eng, w)
+    calls = json.loads(str(z["calls"]))
+    for i, c in enumerate(calls):
+        if c["op"] == "forward":
+            nd = len(c["dec_lens"])
+            prompts = c["input_ids"][: len(c["input_ids"]) - nd]
+            psids = c["seq_ids"][: len(prompts)]
+            for p, s in zip(prompts, psids):
+                for pos in range(0, max(len(p) - 7, 0), 7):
+                    if pos + 7 < len(p):
+                        m.forward([p[pos:pos + 7]], [s], [], prefill_prefix_lens_list=[pos])
+            last_start = [((len(p) - 1) // 7) * 7 if len(p) > 7 else 0 for p in prompts]
+            ids = [p[a:] for p, a in zip(prompts, last_start)] + c["input_ids"][len(prompts):]
+            toks = m.forward(ids, c["seq_ids"], c["dec_lens"], prefill_prefix_lens_list=last_start if prompts else None)
+            ref = torch.from_numpy(z[f"t{i}_logits"]).float()
+            got = m.post_layer.last_logits.float().cpu()
+            assert float((got - ref).abs().max()) <= 4e-3 * float(ref.abs().max())
+            top2 = ref.topk(2, dim=1).values
+            clear = ((top2[:, 0] - top2[:, 1]) > 8e-3 * ref.abs().max()).tolist()
+            for a, b, ok in zip(toks, z[f"t{i}_tokens"].tolist(), clear):
+                assert (not ok) or a == b
+        elif c["op"] == "swap_out":
+            m.swap_out_seqs(c["seq_ids"])
+        elif c["op"] == "swap_in":
+            m.swap_in_seqs(c["seq_ids"])
+        else:
+            m.free_seqs_resources(c["seq_ids"])
