@@ -55,6 +55,8 @@ def parse():
                     help="TP: force NCCL all-reduce + separate add/norm kernel")
     ap.add_argument("--shard-lm-head", action="store_true",
                     help="TP: vocabulary-sharded lm_head + (max, argmax) all-gather instead of a replicated lm_head (opt-in A/B)")
+    ap.add_argument("--fuse-rotary-store", action="store_true",
+                    help="decode: rotary + KV store in one launch per layer (opt-in A/B)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-prefill", action="store_true")
     ap.add_argument("--cpu-sample-seqs", type=int, default=8)
@@ -219,7 +221,7 @@ def run_ours(args):
                                     max_seqs_in_block_table=B, max_blocks_per_seq=blocks_per_seq + 8, max_batch_size=B,
                                     max_tokens_in_batch=max(B, 16384), dtype="bfloat16", tp_size=n, tp_rank=rank,
                                     use_cuda_graph=not args.no_graph, fused_allreduce=args.fused_allreduce,
-                                    shard_lm_head=args.shard_lm_head)
+                                    shard_lm_head=args.shard_lm_head, fuse_rotary_store=args.fuse_rotary_store)
     model = swiftllm_b200.LlamaModel(ec, mc)
     model.load_weights(synthetic_getter(seed=0, std=0.02, device=dev))
     num_blocks = B * blocks_per_seq + 64

@@ -69,6 +69,17 @@ int sllm_store_kvcache(const void* k, const void* v, void* k_cache, void* v_cach
                        int num_layers, int num_kv_heads, int block_size, int head_dim, int max_blocks_per_seq,
                        int64_t k_row_stride, int64_t v_row_stride, sllm_dtype_t dtype, sllm_stream_t stream);
 
+/* ---- Decode-step fusion (new): rotary_embedding_inplace (rotary_emb.py:44-58) + the decode part of store_kvcache
+ * (kvcache_mgmt.py:50-79) in ONE launch for a batch of decoding rows only: q [Bd, nq, D] and k [Bd, nkv, D] rotated in place
+ * with cos/sin [Bd, D/2]; the rotated k row and the v row of sequence i are written to position decoding_seq_lens[i] - 1 of
+ * block-table row seq_ids[i].  Same results, bit for bit, as the two separate calls. */
+int sllm_rotary_store_kvcache_decode(void* q, void* k, const void* v, const void* cos, const void* sin, void* k_cache,
+                                     void* v_cache, const int32_t* block_table, const int32_t* seq_ids,
+                                     const int32_t* decoding_seq_lens, int num_decoding_seqs, int cur_layer,
+                                     int num_layers, int num_q_heads, int num_kv_heads, int block_size, int head_dim,
+                                     int max_blocks_per_seq, int64_t q_row_stride, int64_t k_row_stride,
+                                     int64_t v_row_stride, sllm_dtype_t dtype, sllm_stream_t stream);
+
 /* ---- Paged (decode) attention: swiftllm/worker/kernels/paged_attn.py:152-222 (paged_attention)
  * q [Bd, nq, D]; o [Bd, nq*D]; seq_ids = infer_state.seq_ids[num_prefill_seqs:]; seq_lens = decoding_seq_lens.
  * seq_block_size: tokens per flash-decoding split (multiple of block_size); 0 = let the library choose

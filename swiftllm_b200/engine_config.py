@@ -35,6 +35,9 @@ class EngineConfig:
     # tiny all-gather of per-rank (max logit, argmax) pairs) instead of replicating the 1 GB matrix on every rank.
     # SURVEY.md §8 f-3.  Opt-in until it has been measured on a multi-GPU box.
     shard_lm_head: bool = False
+    # pure-decode steps: rotary embedding + KV store of the new rows in ONE launch per layer instead of two.
+    # Opt-in until it has run on a GPU.
+    fuse_rotary_store: bool = False
 
     @staticmethod
     def add_cli_args(parser: argparse.ArgumentParser):

@@ -12,7 +12,7 @@ import torch
 import torch.distributed as dist
 
 from swiftllm_b200.worker.infer_state import LlamaInferState
-from swiftllm_b200.worker.kernels.kvcache_mgmt import store_kvcache
+from swiftllm_b200.worker.kernels.kvcache_mgmt import rotary_store_kvcache_decode, store_kvcache
 from swiftllm_b200.worker.kernels.linear import linear
 from swiftllm_b200.worker.kernels.paged_attn import paged_attention
 from swiftllm_b200.worker.kernels.prefill_attn import prefill_attention, prefill_attention_paged
@@ -31,6 +31,7 @@ class LlamaTransformerLayer:
         self.layer_id = layer_id
         self.tp_size = getattr(engine_config, "tp_size", 1)
         self.tp_group = tp_group
+        self.fuse_rotary_store = bool(getattr(engine_config, "fuse_rotary_store", False))
         self.comm = comm            # FusedAllReduce (tp_comm.py) or None -> NCCL all-reduce + separate add/norm kernels
         self.num_q_heads = model_config.num_q_heads // self.tp_size      # per-rank shard
         self.num_kv_heads = model_config.num_kv_heads // self.tp_size
@@ -65,10 +66,13 @@ class LlamaTransformerLayer:
         k = qkv[:, nqd:nqd + nkvd].unflatten(1, (self.num_kv_heads, mc.head_dim))
         v = qkv[:, nqd + nkvd:].unflatten(1, (self.num_kv_heads, mc.head_dim))
 
-        rotary_embedding_inplace(q, k, infer_state)
-
-        if not infer_state.ignore_kvcache:
-            store_kvcache(k, v, k_cache, v_cache, block_table, mc, self.engine_config, infer_state, self.layer_id)
+        if self.fuse_rotary_store and infer_state.num_prefill_seqs == 0 and not infer_state.ignore_kvcache:
+            # pure decode: rotary + KV store of the new rows in one launch
+            rotary_store_kvcache_decode(q, k, v, k_cache, v_cache, block_table, infer_state, self.layer_id)
+        else:
+            rotary_embedding_inplace(q, k, infer_state)
+            if not infer_state.ignore_kvcache:
+                store_kvcache(k, v, k_cache, v_cache, block_table, mc, self.engine_config, infer_state, self.layer_id)
 
         npt = infer_state.num_prefill_tokens
         o = input_embds if self.tp_size == 1 else torch.empty((q.shape[0], self.num_q_heads * mc.head_dim),

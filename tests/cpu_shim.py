@@ -63,6 +63,13 @@ def _store_kvcache(k, v, k_cache, v_cache, block_table, model_config, engine_con
                             k_cache.shape[3], cur_layer, **kw)
 
 
+def _rotary_store_kvcache_decode(q, k, v, k_cache, v_cache, block_table, st, cur_layer):
+    assert st.num_prefill_seqs == 0
+    _rotary_embedding_inplace(q, k, st)
+    K.store_kvcache_inplace(k, v, k_cache, v_cache, block_table.numpy(), st.seq_ids.tolist(), [], [], st.decoding_seq_lens.tolist(),
+                            0, 0, k_cache.shape[3], cur_layer)
+
+
 def _paged_attention(q, k_cache, v_cache, block_table, model_config, engine_config, st, cur_layer, o):
     out = K.paged_attention_exact(q, k_cache, v_cache, block_table.numpy(), st.seq_ids[st.num_prefill_seqs:].tolist(),
                                   st.decoding_seq_lens.tolist(), st.softmax_scale, k_cache.shape[3], cur_layer, q.dtype)
@@ -162,6 +169,7 @@ _PATCHES = [
     ("swiftllm_b200.worker.layers.transformer_layer", "silu_and_mul_inplace", _silu_and_mul_inplace),
     ("swiftllm_b200.worker.layers.transformer_layer", "store_kvcache", _store_kvcache),
     ("swiftllm_b200.worker.layers.transformer_layer", "paged_attention", _paged_attention),
+    ("swiftllm_b200.worker.layers.transformer_layer", "rotary_store_kvcache_decode", _rotary_store_kvcache_decode),
     ("swiftllm_b200.worker.layers.transformer_layer", "prefill_attention", _prefill_attention),
     ("swiftllm_b200.worker.layers.transformer_layer", "prefill_attention_paged", _prefill_attention_paged),
     ("swiftllm_b200.worker.layers.post_layer", "rmsnorm_inplace", _rmsnorm_inplace),
