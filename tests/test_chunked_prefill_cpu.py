@@ -160,3 +160,46 @@ def test_chunked_replay_of_the_reference_golden_trace(golden):
         else:
             m.free_seqs_resources(c["seq_ids"])
     assert checked == 6
+
+
+def test_piggyback_planner_drives_the_product_to_the_whole_prompt_result():
+    """plan_piggyback_step / apply_step_result (swiftllm_b200/worker/chunking.py, the worker-side half of the hook at
+    scheduler.py:93-94) driving the product on CPU: three prompts under a 24-token step budget with decodes joining as prompts
+    finish.  Every sequence must produce the tokens the oracle produces with whole-prompt prefill followed by decoding."""
+    from swiftllm_b200.worker.chunking import PrefillProgress, apply_step_result, plan_piggyback_step
+    w = OracleWeights.random(CFG, dtype=torch.float16, seed=9, std=0.08)
+    rng = np.random.default_rng(31)
+    prompts = {3: rng.integers(0, 300, size=41).tolist(), 0: rng.integers(0, 300, size=9).tolist(), 5: rng.integers(0, 300, size=30).tolist()}
+    NEW = 4                                                          # tokens to generate per sequence
+    # expected: whole-prompt prefill of each sequence alone, then NEW-1 decode steps
+    expect = {}
+    for sid, p in prompts.items():
+        o = _oracle(w)
+        toks = o.forward([p], [sid], [])
+        for j in range(NEW - 1):
+            toks.append(o.forward([[toks[-1]]], [sid], [len(p) + j + 1])[0])
+        expect[sid] = toks
+    with product_on_cpu():
+        m = _product(w)
+        pending = [PrefillProgress(sid, p) for sid, p in prompts.items()]
+        out = {sid: [] for sid in prompts}
+        lens = {}
+        steps = 0
+        while any(len(v) < NEW for v in out.values()):
+            running = [sid for sid in out if 0 < len(out[sid]) < NEW]
+            for sid in running:
+                lens[sid] += 1
+            step = plan_piggyback_step([p for p in pending if p.remaining > 0], running, [out[s][-1] for s in running],
+                                       [lens[s] for s in running], max_tokens_in_step=24, max_chunk=16)
+            live = [p for p in pending if p.remaining > 0]
+            toks = m.forward(step.input_ids_list, step.seq_ids_list, step.decoding_seq_lens_list,
+                             prefill_prefix_lens_list=step.prefill_prefix_lens_list)
+            assert sum(len(x) for x in step.input_ids_list) <= 24
+            first, dec = apply_step_result(step, live, toks)
+            for sid, t in zip(running, dec):
+                out[sid].append(t)
+            for sid, t in first.items():
+                out[sid].append(t); lens[sid] = len(prompts[sid])
+            steps += 1
+            assert steps < 40
+        assert out == expect
