@@ -191,6 +191,14 @@ int sllm_swap_blocks(const int64_t* host_src_ids, const int64_t* host_dst_ids, i
                      void* k_cache, void* v_cache, void* host_k_swap, void* host_v_swap, int64_t block_bytes,
                      sllm_stream_t stream);
 
+/* Sync-free variant (new): src_ids / dst_ids are DEVICE arrays (int64) - the gathered source ids and the
+ * newly allocated target ids never travel to the host (the reference does `.tolist()` twice per swap, model.py:374-377) - and
+ * one kernel moves every block between the cache and the swap space, which must be pinned, device-mapped host memory
+ * (cudaHostAlloc / torch pin_memory).  Same data movement as sllm_swap_blocks. */
+int sllm_swap_blocks_gathered(const int64_t* src_ids, const int64_t* dst_ids, int64_t n, int is_swap_in, void* k_cache,
+                              void* v_cache, void* host_k_swap, void* host_v_swap, int64_t block_bytes,
+                              sllm_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -7,7 +7,7 @@ mkdir -p gpurun_out
 N=$(nvidia-smi -L | wc -l); echo "gpus: $N"
 export SLLM_RUN_PENDING=1
 echo "== pending 1-GPU tests (chunked prefill: store, paged prefill attention gen1+gen2, model; fused rotary+store)"
-timeout 900 python -m pytest tests/test_chunked_prefill_gpu.py tests/test_decode_fusion_gpu.py -m gpu -q -p no:cacheprovider --maxfail=8 > gpurun_out/pytest_pending_1gpu.log 2>&1; echo "rc=$?"; tail -15 gpurun_out/pytest_pending_1gpu.log | cut -c1-300
+timeout 900 python -m pytest tests/test_chunked_prefill_gpu.py tests/test_decode_fusion_gpu.py tests/test_swap_device_gpu.py -m gpu -q -p no:cacheprovider --maxfail=8 > gpurun_out/pytest_pending_1gpu.log 2>&1; echo "rc=$?"; tail -15 gpurun_out/pytest_pending_1gpu.log | cut -c1-300
 echo "== validated suite still green"
 timeout 1200 python -m pytest tests -m gpu -q -p no:cacheprovider --maxfail=5 > gpurun_out/pytest_all.log 2>&1; echo "rc=$?"; tail -5 gpurun_out/pytest_all.log | cut -c1-300
 echo "== SARATHI bench (configs[2])"

@@ -40,6 +40,7 @@ SIGNATURES = {
     "sllm_allreduce_add_rmsnorm": (_I, [_P, _P, _I, _I, _I, _P, _P, _P, _P, _F, _L, _I, _I, _P]),
     "sllm_allreduce_add_rmsnorm_2shot": (_I, [_P, _P, _P, _I, _I, _I, _P, _P, _P, _F, _L, _I, _I, _P]),
     "sllm_swap_blocks": (_I, [_P, _P, _L, _I, _P, _P, _P, _P, _L, _P]),
+    "sllm_swap_blocks_gathered": (_I, [_P, _P, _L, _I, _P, _P, _P, _P, _L, _P]),
 }
 
 _lib = None

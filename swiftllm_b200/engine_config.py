@@ -38,6 +38,10 @@ class EngineConfig:
     # pure-decode steps: rotary embedding + KV store of the new rows in ONE launch per layer instead of two.
     # Opt-in until it has run on a GPU.
     fuse_rotary_store: bool = False
+    # swap in / out with device-resident id lists and one gather/scatter kernel over the pinned, mapped swap space (no host
+    # syncs) instead of `.tolist()` + cudaMemcpyAsync per run.  Needs pin_swap_space.  Opt-in until it has
+    # run on a GPU.
+    device_swap: bool = False
 
     @staticmethod
     def add_cli_args(parser: argparse.ArgumentParser):

@@ -398,8 +398,13 @@ class LlamaModel:
         src_block_ids = src.gather_allocated_blocks_and_free(seq_ids, seq_ids_list=seq_ids_list)
         dst_block_ids = dst.allocate_blocks_for_seqs(seq_ids, seq_lengths, seq_ids_list=seq_ids_list,
                                                      target_lens_list=seq_lengths_list)
-        swiftllm_c.swap_blocks(src_block_ids.tolist(), dst_block_ids.tolist(), is_swap_in,
-                               self.k_cache, self.v_cache, self.k_swap, self.v_swap)
+        if getattr(self.engine_config, "device_swap", False):
+            # ids stay on the device, one gather/scatter kernel over the mapped swap space: the whole swap is sync-free
+            swiftllm_c.swap_blocks_device(src_block_ids.to(torch.int64), dst_block_ids, is_swap_in,
+                                          self.k_cache, self.v_cache, self.k_swap, self.v_swap)
+        else:
+            swiftllm_c.swap_blocks(src_block_ids.tolist(), dst_block_ids.tolist(), is_swap_in,
+                                   self.k_cache, self.v_cache, self.k_swap, self.v_swap)
 
     @torch.inference_mode()
     def swap_in_seqs(self, seq_ids_list: list):

@@ -163,6 +163,11 @@ class GlooFusedAllReduce:
         return out
 
 
+def _swap_blocks_device(src_ids, dst_ids, is_swap_in, k_cache, v_cache, k_swap, v_swap):
+    assert src_ids.dtype == torch.int64 and dst_ids.dtype == torch.int64
+    K.swap_blocks_inplace(src_ids.tolist(), dst_ids.tolist(), is_swap_in, k_cache, v_cache, k_swap, v_swap)
+
+
 _PATCHES = [
     ("swiftllm_b200.worker.layers.transformer_layer", "fused_add_rmsnorm_inplace", _fused_add_rmsnorm_inplace),
     ("swiftllm_b200.worker.layers.transformer_layer", "rotary_embedding_inplace", _rotary_embedding_inplace),
@@ -177,6 +182,7 @@ _PATCHES = [
     ("swiftllm_b200.worker.block_manager", "unset_block_table_and_num_seq_alloc_blocks", _unset),
     ("swiftllm_b200.worker.block_manager", "gather_allocated_blocks_and_unset", _gather_and_unset),
     ("swiftllm_b200.swiftllm_c", "swap_blocks", _swap_blocks),
+    ("swiftllm_b200.swiftllm_c", "swap_blocks_device", _swap_blocks_device),
 ]
 
 

@@ -62,16 +62,17 @@ def _same_state(m, o):
 import pytest
 
 
-@pytest.mark.parametrize("fuse_rotary_store", [False, True], ids=["separate-rotary-store", "fused-rotary-store"])
-def test_product_host_path_matches_oracle_on_cpu(fuse_rotary_store):
+@pytest.mark.parametrize("fuse_rotary_store,device_swap", [(False, False), (True, True)], ids=["reference-shaped", "fused-rotary-store+device-swap"])
+def test_product_host_path_matches_oracle_on_cpu(fuse_rotary_store, device_swap):
     """Prefill, decode, a mixed batch, swap out / in, free.  Same oracle kernels on both sides, so the only arithmetic difference
     is the fused QKV GEMM: logits within 1e-5 of max|logit|, greedy tokens, every block id, free map and host mirror identical.
-    fuse_rotary_store: pure-decode steps take the one-launch rotary + KV-store path, mixed / prefill steps the separate calls."""
+    fuse_rotary_store: pure-decode steps take the one-launch rotary + KV-store path, mixed / prefill steps the separate calls;
+    device_swap: swap_out / swap_in hand device-resident id tensors to the gather/scatter swap entry (no .tolist())."""
     torch.manual_seed(0)
     w = OracleWeights.random(CFG, dtype=torch.float16, seed=2, std=0.08)
     rng = np.random.default_rng(5)
     with product_on_cpu():
-        m, o = _product(w, fuse_rotary_store=fuse_rotary_store), _oracle(w)
+        m, o = _product(w, fuse_rotary_store=fuse_rotary_store, device_swap=device_swap), _oracle(w)
 
         def step(*a):
             tm, to = m.forward(*a), o.forward(*a)
