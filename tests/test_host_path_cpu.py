@@ -111,3 +111,53 @@ def test_product_block_exhaustion_raises_like_the_reference():
         with pytest.raises(RuntimeError, match="No enough free blocks"):
             m.forward([[1] * 120, [2] * 120, [3] * 120, [4] * 120], [0, 1, 2, 3], [])      # 4 x 8 blocks > 24
         assert m.gpu_block_manager.num_free_blocks == ENG["num_blocks"]                     # nothing was taken
+
+
+def test_block_manager_random_operation_sequences_match_the_oracle():
+    """Seeded random walks over the product BlockManager's API (allocate to a larger target - as decode and chunked prefill do -,
+    free, gather-and-free, exhaustion) against the numpy restatement of the reference's BlockManager (block_manager.py:5-103):
+    block ids handed out, tables, free map, free count and the host mirror must agree after every operation, and a failed
+    allocation must change nothing."""
+    from swiftllm_b200.worker.block_manager import BlockManager
+    from oracle.kernels import BlockManagerOracle
+    import pytest
+    with product_on_cpu():
+        for seed in range(6):
+            rng = np.random.default_rng(seed)
+            nblk, nseq, mbps, bs = int(rng.integers(8, 40)), 10, 12, 16
+            bm = BlockManager("GPU", nblk, nseq, mbps, bs, device="cpu")
+            ob = BlockManagerOracle(nblk, nseq, mbps, bs)
+            lens = np.zeros(nseq, dtype=np.int64)
+            for _ in range(120):
+                op = rng.choice(["alloc", "alloc", "alloc", "free", "gather"])
+                k = int(rng.integers(1, 5))
+                sids = rng.choice(nseq, size=k, replace=False).tolist()
+                t_s = torch.tensor(sids, dtype=torch.int32)
+                if op == "alloc":
+                    grow = rng.integers(0, 40, size=k)
+                    target = np.minimum(lens[sids] + grow, mbps * bs).tolist()
+                    t_l = torch.tensor(target, dtype=torch.int32)
+                    need = int(sum((t + bs - 1) // bs for t in target) - ob.num_seq_allocated_blocks[sids].sum())
+                    if need > ob.num_free_blocks:
+                        free_before = bm.is_block_free.clone()
+                        with pytest.raises(RuntimeError, match="No enough free blocks"):
+                            bm.allocate_blocks_for_seqs(t_s, t_l, seq_ids_list=sids, target_lens_list=target)
+                        with pytest.raises(RuntimeError):
+                            ob.allocate_blocks_for_seqs(sids, target)
+                        assert torch.equal(bm.is_block_free, free_before)
+                    else:
+                        new = bm.allocate_blocks_for_seqs(t_s, t_l, seq_ids_list=sids, target_lens_list=target)
+                        ref = ob.allocate_blocks_for_seqs(sids, target)
+                        assert new.tolist() == ref.tolist()
+                        lens[sids] = target
+                elif op == "free":
+                    bm.free_blocks_for_seqs(t_s, seq_ids_list=sids); ob.free_blocks_for_seqs(sids); lens[sids] = 0
+                else:
+                    got = bm.gather_allocated_blocks_and_free(t_s, seq_ids_list=sids)
+                    assert got.tolist() == ob.gather_allocated_blocks_and_free(sids).tolist()
+                    lens[sids] = 0
+                n = ob.num_seq_allocated_blocks
+                assert np.array_equal(bm.num_seq_allocated_blocks.numpy(), n) and np.array_equal(bm._host_nsab, n)
+                assert np.array_equal(bm.is_block_free.numpy(), ob.is_block_free) and bm.num_free_blocks == ob.num_free_blocks
+                for s in range(nseq):
+                    assert np.array_equal(bm.block_table.numpy()[s, : n[s]], ob.block_table[s, : n[s]])
