@@ -51,6 +51,8 @@ def parse():
                     help="TP: force the one-shot peer-memory all-reduce fused with add+RMSNorm (default: automatic, tp 2..4)")
     ap.add_argument("--two-shot-allreduce", dest="fused_allreduce", action="store_const", const="two_shot",
                     help="TP: the row-owner (reduce-scatter + all-gather) variant of the fused exchange (meant for tp 8)")
+    ap.add_argument("--nvls-allreduce", dest="fused_allreduce", action="store_const", const="two_shot_nvls",
+                    help="TP: two-shot fused exchange with in-switch reduction / broadcast (multimem.ld_reduce / multimem.st)")
     ap.add_argument("--nccl-allreduce", dest="fused_allreduce", action="store_false",
                     help="TP: force NCCL all-reduce + separate add/norm kernel")
     ap.add_argument("--shard-lm-head", action="store_true",
@@ -374,7 +376,8 @@ def run_ours(args):
                      "algorithmic_bytes_per_launch": alg_bytes, "mean_launch_ms": pa_ms, "launches_timed": len(durs),
                      "how": "CUDA events around every paged_attention launch over K eager decode steps on the launching stream"},
         "tp_exchange": None if n == 1 else (
-            ("fused peer-memory reduce-scatter + add + rmsnorm + all-gather (one kernel, two-shot)" if model.comm.two_shot
+            ("fused NVLS reduce-scatter + add + rmsnorm + all-gather (one kernel, two-shot, multimem)" if getattr(model.comm, "nvls", False)
+             else "fused peer-memory reduce-scatter + add + rmsnorm + all-gather (one kernel, two-shot)" if model.comm.two_shot
              else "fused peer-memory all-reduce + add + rmsnorm (one kernel)") if model.comm is not None
             else "ncclAllReduce + fused_add_rmsnorm"),
         "lm_head": "vocabulary-sharded (all-gather of per-rank argmax)" if (n > 1 and args.shard_lm_head) else "replicated",

@@ -177,11 +177,14 @@ int sllm_allreduce_add_rmsnorm(const void* const* host_peer_bufs, void* const* h
  * only, which then stores the normalised row into EVERY rank's x_out buffer (host_peer_xout: HOST array of `nranks` DEVICE
  * pointers, symmetric memory like the partial buffers; the result appears in this rank's own buffer when the call's kernel
  * has finished).  Remote traffic per rank 2*(N-1)/N*T*H instead of (N-1)*T*H bytes; two flag barriers (signal-pad rows
- * `slot` and 8 + `slot`, slot < 8).  `residual` is only maintained for the rows this rank owns; weight is required. */
+ * `slot` and 8 + `slot`, slot < 8).  `residual` is only maintained for the rows this rank owns; weight is required.
+ * mc_buf / mc_xout: NVLS multicast addresses (DEVICE pointers) of the partial buffer of this slot and of x_out, or both NULL.
+ * When given, the reduction is ONE multimem.ld_reduce per 16 bytes (the NVSwitch sums all ranks' copies, fp32 accumulation)
+ * and the broadcast ONE multimem.st, instead of N peer loads / stores. */
 int sllm_allreduce_add_rmsnorm_2shot(const void* const* host_peer_bufs, void* const* host_peer_xout,
-                                     void* const* host_peer_flags, int rank, int nranks, int slot, void* epoch_state,
-                                     void* residual, const void* weight, float eps, int64_t num_tokens, int hidden,
-                                     sllm_dtype_t dtype, sllm_stream_t stream);
+                                     void* const* host_peer_flags, const void* mc_buf, void* mc_xout, int rank, int nranks,
+                                     int slot, void* epoch_state, void* residual, const void* weight, float eps,
+                                     int64_t num_tokens, int hidden, sllm_dtype_t dtype, sllm_stream_t stream);
 
 /* ---- Block swapping: csrc/src/block_swapping.cpp:22-85 (swiftllm_c.swap_blocks, csrc/src/entrypoints.cpp:5-7)
  * host_src_ids/host_dst_ids: HOST arrays of n block ids.  k_swap/v_swap: HOST memory (pinned or pageable),

@@ -11,6 +11,8 @@
 // consecutive exchanges, so a rank can only overwrite a buffer after every peer has passed the barrier of the
 // exchange in between, i.e. finished reading it.  Epochs live in device memory (CUDA-graph replay safe).
 // A watchdog traps instead of hanging if a peer never arrives.
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace sllm {
@@ -122,6 +124,8 @@ __global__ void __launch_bounds__(512) allreduce_add_rmsnorm_kernel(const ArPara
 // pushes the normalised row into every rank's x_out buffer (P2P stores).  Remote traffic per rank: 2 * (N-1)/N * T * H bytes,
 // 4x less than one-shot at N = 8.  Two barriers per exchange, both flag-based over peer memory:
 //   A  "my partial is complete"           (as above: published by CTA 0, awaited by every CTA)
+// With NVLS = true the N peer loads become ONE multimem.ld_reduce on the multicast address of the partial buffer (the NVSwitch
+// sums the N copies with fp32 accumulation) and the N peer stores ONE multimem.st on the multicast address of x_out.
 //   B  "my rows have landed everywhere"   published by the LAST CTA of a rank to finish (after a system fence), and awaited by
 //      that same CTA for all ranks before the kernel may end - so the next kernel in the stream sees the whole x_out.
 // A single x_out buffer per rank suffices: a peer can only write exchange k+1's rows after barrier A of k+1, i.e. after this
@@ -134,14 +138,40 @@ struct Ar2Params {
     void* residual; const void* weight;
     float eps;
     int rank, nranks, hidden, slot, num_tokens;
+    // NVLS (template NVLS = true): multicast addresses of the partial buffer (this slot) and of x_out.  One
+    // multimem.ld_reduce replaces the N peer loads (the NVSwitch sums the N copies, fp32 accumulation), one multimem.st the N
+    // peer stores (the switch broadcasts).
+    const void* mc_buf; void* mc_xout;
 };
+
+// 8 x 16-bit values summed over all GPUs of the multicast group by the switch (fp32 accumulation, one rounding)
+template <typename T> __device__ __forceinline__ Vec8<T> multimem_ld_reduce_add(const T* mc);
+template <> __device__ __forceinline__ Vec8<__half> multimem_ld_reduce_add<__half>(const __half* mc) {
+    uint4 u;
+    asm volatile("multimem.ld_reduce.relaxed.sys.global.add.acc::f32.v4.f16x2 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(u.x), "=r"(u.y), "=r"(u.z), "=r"(u.w) : "l"(mc) : "memory");
+    return *reinterpret_cast<Vec8<__half>*>(&u);
+}
+template <> __device__ __forceinline__ Vec8<__nv_bfloat16> multimem_ld_reduce_add<__nv_bfloat16>(const __nv_bfloat16* mc) {
+    uint4 u;
+    asm volatile("multimem.ld_reduce.relaxed.sys.global.add.acc::f32.v4.bf16x2 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(u.x), "=r"(u.y), "=r"(u.z), "=r"(u.w) : "l"(mc) : "memory");
+    return *reinterpret_cast<Vec8<__nv_bfloat16>*>(&u);
+}
+template <typename T> __device__ __forceinline__ void multimem_st(T* mc, const Vec8<T>& v) {
+    const uint4 u = *reinterpret_cast<const uint4*>(&v);
+    if constexpr (sizeof(T) == 2 && std::is_same<T, __half>::value)
+        asm volatile("multimem.st.relaxed.sys.global.v4.f16x2 [%0], {%1,%2,%3,%4};" ::"l"(mc), "r"(u.x), "r"(u.y), "r"(u.z), "r"(u.w) : "memory");
+    else
+        asm volatile("multimem.st.relaxed.sys.global.v4.bf16x2 [%0], {%1,%2,%3,%4};" ::"l"(mc), "r"(u.x), "r"(u.y), "r"(u.z), "r"(u.w) : "memory");
+}
 
 template <typename T> __device__ __forceinline__ void st_vec8_peer(T* p, const Vec8<T>& v) {
     const uint4 u = *reinterpret_cast<const uint4*>(&v);
     asm volatile("st.global.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(u.x), "r"(u.y), "r"(u.z), "r"(u.w) : "memory");
 }
 
-template <typename T>
+template <typename T, bool NVLS>
 __global__ void __launch_bounds__(512) allreduce_add_rmsnorm_2shot_kernel(const Ar2Params p) {
     extern __shared__ uint4 row_smem[];
     __shared__ float red[16];
@@ -170,16 +200,23 @@ __global__ void __launch_bounds__(512) allreduce_add_rmsnorm_2shot_kernel(const 
         T* rr = reinterpret_cast<T*>(p.residual) + t * p.hidden;
         float ss = 0.f;
         for (int i = threadIdx.x; i < nvec; i += blockDim.x) {
-            float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            Vec8<T> sum;                                            // h(sum over ranks)
+            if constexpr (NVLS) {
+                sum = multimem_ld_reduce_add<T>(reinterpret_cast<const T*>(p.mc_buf) + t * p.hidden + 8 * i);
+            } else {
+                float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll 1
-            for (int r = 0; r < p.nranks; r++) {
-                Vec8<T> v = ld_vec8_peer(reinterpret_cast<const T*>(p.peer_buf[r]) + t * p.hidden + 8 * i);
+                for (int r = 0; r < p.nranks; r++) {
+                    Vec8<T> v = ld_vec8_peer(reinterpret_cast<const T*>(p.peer_buf[r]) + t * p.hidden + 8 * i);
 #pragma unroll
-                for (int j = 0; j < 4; j++) { float2 f = TT::to_f2(v.v[j]); acc[2 * j] += f.x; acc[2 * j + 1] += f.y; }
+                    for (int j = 0; j < 4; j++) { float2 f = TT::to_f2(v.v[j]); acc[2 * j] += f.x; acc[2 * j + 1] += f.y; }
+                }
+#pragma unroll
+                for (int j = 0; j < 4; j++) sum.v[j] = TT::from_f2(make_float2(acc[2 * j], acc[2 * j + 1]));
             }
             Vec8<T> a, b = ld_vec8(rr + 8 * i);
 #pragma unroll
-            for (int j = 0; j < 4; j++) a.v[j] = __hadd2_rn(TT::from_f2(make_float2(acc[2 * j], acc[2 * j + 1])), b.v[j]);   // h(h(sum) + r)
+            for (int j = 0; j < 4; j++) a.v[j] = __hadd2_rn(sum.v[j], b.v[j]);   // h(h(sum) + r)
             st_vec8(rr + 8 * i, a);
             row_smem[i] = *reinterpret_cast<uint4*>(&a);
 #pragma unroll
@@ -204,11 +241,15 @@ __global__ void __launch_bounds__(512) allreduce_add_rmsnorm_2shot_kernel(const 
             }
             // ---- all-gather: the normalised row goes to every rank (own copy included), starting with the next rank so the
             // N owners do not all hit the same destination at the same time
+            if constexpr (NVLS) {
+                multimem_st<T>(reinterpret_cast<T*>(p.mc_xout) + t * p.hidden + 8 * i, o);
+            } else {
 #pragma unroll 1
-            for (int k = 0; k < p.nranks; k++) {
-                int r = p.rank + 1 + k;
-                if (r >= p.nranks) r -= p.nranks;
-                st_vec8_peer(reinterpret_cast<T*>(p.peer_xout[r]) + t * p.hidden + 8 * i, o);
+                for (int k = 0; k < p.nranks; k++) {
+                    int r = p.rank + 1 + k;
+                    if (r >= p.nranks) r -= p.nranks;
+                    st_vec8_peer(reinterpret_cast<T*>(p.peer_xout[r]) + t * p.hidden + 8 * i, o);
+                }
             }
         }
     }
@@ -243,10 +284,13 @@ using namespace sllm;
 // Two-shot variant: see the kernel comment.  host_peer_xout: HOST array of `nranks` device pointers to every rank's x_out
 // buffer [>= num_tokens, hidden] (symmetric memory); the normalised activations appear in THIS rank's buffer.  `residual` is
 // only maintained for the rows this rank owns (t % nranks == rank); weight is required.  slot < 8.
+// mc_buf / mc_xout: multicast (NVLS) addresses of the partial buffer of this slot and of x_out, or NULL for peer loads / stores.
 extern "C" int sllm_allreduce_add_rmsnorm_2shot(const void* const* host_peer_bufs, void* const* host_peer_xout,
-                                                void* const* host_peer_flags, int rank, int nranks, int slot, void* epoch_state,
-                                                void* residual, const void* weight, float eps, int64_t num_tokens, int hidden,
-                                                sllm_dtype_t dtype, sllm_stream_t stream) {
+                                                void* const* host_peer_flags, const void* mc_buf, void* mc_xout, int rank,
+                                                int nranks, int slot, void* epoch_state, void* residual, const void* weight,
+                                                float eps, int64_t num_tokens, int hidden, sllm_dtype_t dtype,
+                                                sllm_stream_t stream) {
+    SLLM_REQUIRE((mc_buf == nullptr) == (mc_xout == nullptr), "allreduce(2-shot): give both multicast addresses or neither");
     SLLM_REQUIRE(nranks >= 2 && nranks <= AR_MAX_RANKS && rank >= 0 && rank < nranks, "allreduce(2-shot): bad rank %d of %d", rank, nranks);
     SLLM_REQUIRE(slot >= 0 && slot < 8, "allreduce(2-shot): bad slot %d", slot);
     SLLM_REQUIRE(hidden > 0 && hidden % 8 == 0 && num_tokens >= 0 && num_tokens < (1LL << 31),
@@ -259,21 +303,27 @@ extern "C" int sllm_allreduce_add_rmsnorm_2shot(const void* const* host_peer_buf
     }
     p.epoch = (uint32_t*)epoch_state; p.residual = residual; p.weight = weight; p.eps = eps;
     p.rank = rank; p.nranks = nranks; p.hidden = hidden; p.slot = slot; p.num_tokens = (int)num_tokens;
+    p.mc_buf = mc_buf; p.mc_xout = mc_xout;
+    const bool nvls = mc_buf != nullptr;
     const int nvec = hidden / 8;
     int threads = nvec >= 512 ? 512 : (nvec >= 256 ? 256 : ((nvec + 31) / 32) * 32);
     if (threads < 32) threads = 32;
     const size_t smem = (size_t)nvec * sizeof(uint4);
     const unsigned grid = (unsigned)((num_tokens + nranks - 1) / nranks);        // the same on every rank
     cudaStream_t st = (cudaStream_t)stream;
+#define SLLM_AR2_LAUNCH(TT, NV)                                                                                                   \
+    do {                                                                                                                          \
+        if (smem > 48 * 1024) cudaFuncSetAttribute(allreduce_add_rmsnorm_2shot_kernel<TT, NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+        allreduce_add_rmsnorm_2shot_kernel<TT, NV><<<grid, threads, smem, st>>>(p);                                               \
+    } while (0)
     if (dtype == SLLM_F16) {
-        if (smem > 48 * 1024) cudaFuncSetAttribute(allreduce_add_rmsnorm_2shot_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        allreduce_add_rmsnorm_2shot_kernel<__half><<<grid, threads, smem, st>>>(p);
+        if (nvls) SLLM_AR2_LAUNCH(__half, true); else SLLM_AR2_LAUNCH(__half, false);
     } else if (dtype == SLLM_BF16) {
-        if (smem > 48 * 1024) cudaFuncSetAttribute(allreduce_add_rmsnorm_2shot_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        allreduce_add_rmsnorm_2shot_kernel<__nv_bfloat16><<<grid, threads, smem, st>>>(p);
+        if (nvls) SLLM_AR2_LAUNCH(__nv_bfloat16, true); else SLLM_AR2_LAUNCH(__nv_bfloat16, false);
     } else {
         SLLM_REQUIRE(false, "allreduce(2-shot): unknown dtype tag %d", (int)dtype);
     }
+#undef SLLM_AR2_LAUNCH
     return check_launch("allreduce_add_rmsnorm_2shot");
 }
 

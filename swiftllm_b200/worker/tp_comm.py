@@ -26,13 +26,15 @@ class FusedAllReduce:
     residual is only kept up to date for the rows a rank owns and `reduce_add_norm` returns a view of a symmetric buffer that
     is overwritten by the next exchange."""
 
-    def __init__(self, max_tokens: int, hidden: int, dtype: torch.dtype, device, group=None, two_shot: bool = False):
+    def __init__(self, max_tokens: int, hidden: int, dtype: torch.dtype, device, group=None, two_shot: bool = False,
+                 nvls: bool = False):
         import torch.distributed._symmetric_memory as symm_mem
         group = group if group is not None else dist.group.WORLD
         self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
         assert 2 <= self.world <= 8
         self.max_tokens, self.hidden, self.dtype, self.device = max_tokens, hidden, dtype, device
-        self.two_shot = bool(two_shot)
+        self.two_shot = bool(two_shot) or bool(nvls)
+        self.nvls = bool(nvls)          # two-shot with in-switch reduction / broadcast (multimem.ld_reduce / multimem.st)
         self.data = symm_mem.empty((NUM_SLOTS, max_tokens, hidden), dtype=dtype, device=device)
         self.flags = symm_mem.empty((16 * 8,), dtype=torch.int32, device=device)
         self.data.zero_(); self.flags.zero_()
@@ -48,6 +50,14 @@ class FusedAllReduce:
         self._buf_ptrs = [PtrArr(*[int(p) + s * slot_bytes for p in self._hd.buffer_ptrs]) for s in range(NUM_SLOTS)]
         self._flag_ptrs = PtrArr(*[int(p) for p in self._hf.buffer_ptrs])
         self._xout_ptrs = PtrArr(*[int(p) for p in self._hx.buffer_ptrs]) if self.two_shot else None
+        self._mc_buf = [0] * NUM_SLOTS
+        self._mc_xout = 0
+        if self.nvls:
+            mc_d, mc_x = int(self._hd.multicast_ptr or 0), int(self._hx.multicast_ptr or 0)
+            if mc_d == 0 or mc_x == 0:
+                raise RuntimeError("NVLS multicast addresses unavailable for the symmetric buffers (no multicast support)")
+            self._mc_buf = [mc_d + s * slot_bytes for s in range(NUM_SLOTS)]
+            self._mc_xout = mc_x
         self.epoch = torch.zeros((32,), dtype=torch.int32, device=device)
 
     def partial_out(self, slot: int, num_tokens: int) -> torch.Tensor:
@@ -62,7 +72,8 @@ class FusedAllReduce:
             assert weight is not None and num_tokens <= self.max_tokens
             _lib.check(_lib.lib().sllm_allreduce_add_rmsnorm_2shot(
                 ctypes.cast(self._buf_ptrs[slot], ctypes.c_void_p), ctypes.cast(self._xout_ptrs, ctypes.c_void_p),
-                ctypes.cast(self._flag_ptrs, ctypes.c_void_p), self.rank, self.world, slot, self.epoch.data_ptr(),
+                ctypes.cast(self._flag_ptrs, ctypes.c_void_p), self._mc_buf[slot], self._mc_xout, self.rank, self.world, slot,
+                self.epoch.data_ptr(),
                 residual.data_ptr(), weight.data_ptr(), eps, num_tokens, self.hidden, _lib.dtype_tag(self.dtype),
                 _lib.stream()), "allreduce_add_rmsnorm_2shot")
             return self.xout[:num_tokens]

@@ -32,7 +32,7 @@ def _run(rank, world, port, q):
         m.init_kvcache_and_swap(40)
         m.post_layer.keep_logits = True
         return m
-    fused = {"0": False, "1": True, "2": "two_shot"}[os.environ.get("SLLM_TEST_FUSED_AR", "0")]
+    fused = {"0": False, "1": True, "2": "two_shot", "3": "two_shot_nvls"}[os.environ.get("SLLM_TEST_FUSED_AR", "0")]
     tp = make(world, rank, fused=fused)
     tpg = make(world, rank, graph=True, fused=fused)
     ref = make(1, 0) if rank == 0 else None
@@ -123,19 +123,21 @@ def test_tp_vocab_sharded_lm_head_matches_single_gpu(world, monkeypatch):
 
 
 @pytest.mark.pending_gpu
+@pytest.mark.parametrize("mode", ["2", "3"], ids=["p2p", "nvls-multimem"])
 @pytest.mark.parametrize("world", [2, 4])
-def test_tp_two_shot_fused_exchange_matches_single_gpu(world, monkeypatch):
+def test_tp_two_shot_fused_exchange_matches_single_gpu(world, mode, monkeypatch):
     """fused_allreduce="two_shot" (row owner reduces + adds + normalises, pushes the row to every rank; residual sharded by
     rows) against the TP=1 model, eager and inside CUDA graphs; prompts of 40 / 7 / 129 tokens exercise rows without an owner
-    CTA on some ranks and T not divisible by the world size.  PENDING first GPU run."""
+    CTA on some ranks and T not divisible by the world size.  nvls-multimem: the reduction and the broadcast done by the NVSwitch
+    (multimem.ld_reduce / multimem.st on the symmetric buffers' multicast addresses).  PENDING first GPU run."""
     if torch.cuda.device_count() < world:
         pytest.skip(f"needs {world} GPUs")
-    monkeypatch.setenv("SLLM_TEST_FUSED_AR", "2")
+    monkeypatch.setenv("SLLM_TEST_FUSED_AR", mode)
     monkeypatch.setenv("SLLM_TEST_SHARD_LM_HEAD", "0")
     import torch.multiprocessing as mp
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    procs = [ctx.Process(target=_run, args=(r, world, 29720 + world, q)) for r in range(world)]
+    procs = [ctx.Process(target=_run, args=(r, world, 29720 + world + 10 * int(mode), q)) for r in range(world)]
     for p in procs:
         p.start()
     worst = q.get(timeout=300)
