@@ -36,7 +36,7 @@ __global__ void __launch_bounds__(PF_THREADS, 1) prefill_attn_kernel(
     constexpr int CPR = D / 8;
     constexpr int Q_BYTES = PF_BQ * D * 2;
     constexpr int KV_BYTES = PF_BK * D * 2;
-    extern __shared__ __align__(128) uint8_t smem[];   // [Q tile][stage0: K,V][stage1: K,V]
+    extern __shared__ __align__(128) uint8_t pf_smem[];   // [Q tile][stage0: K,V][stage1: K,V]
 
     const int qb = gridDim.x - 1 - blockIdx.x;          // heaviest (latest) query blocks first
     const int head = blockIdx.y, seq = blockIdx.z;
@@ -55,8 +55,8 @@ __global__ void __launch_bounds__(PF_THREADS, 1) prefill_attn_kernel(
     const int32_t* bt = PAGED ? pk.block_table + (int64_t)pk.seq_ids[seq] * pk.max_blocks_per_seq : nullptr;
     const int64_t os = (int64_t)nq * D;
 
-    const uint32_t q_sm = smem_u32(smem);
-    auto kv_sm = [&](int stage) { return smem_u32(smem + Q_BYTES + stage * 2 * KV_BYTES); };
+    const uint32_t q_sm = smem_u32(pf_smem);
+    auto kv_sm = [&](int stage) { return smem_u32(pf_smem + Q_BYTES + stage * 2 * KV_BYTES); };
 
     // Q tile -> smem (rows past the sequence end are zero-filled)
 #pragma unroll
