@@ -6,6 +6,8 @@ line with the mean step time over whole prompts (8 chunk positions each), tokens
 same schedule with the chunk and the decodes issued as two separate calls (what the reference would have to do).
 
     python scripts/sarathi_bench.py [--chunk 512] [--decodes 64] [--prompt 4096] [--prompts 3]
+    torchrun --nproc-per-node 8 scripts/sarathi_bench.py --gpus 8 --model llama3-70b --prompt 8192 --seqlen 8192
+        (BASELINE.json configs[4]: Llama-3-70B, TP = 8, mixed prefill/decode at seq_len 8192)
 """
 import argparse
 import json
@@ -26,21 +28,29 @@ def main():
     ap.add_argument("--seqlen", type=int, default=4096)
     ap.add_argument("--prompts", type=int, default=3, help="timed prompts (each = prompt/chunk steps); one more runs as warm-up")
     ap.add_argument("--layers", type=int, default=0)
+    ap.add_argument("--gpus", type=int, default=1, help="tensor-parallel degree (launch with torchrun --nproc-per-node N)")
+    ap.add_argument("--model", type=str, default="llama3-8b", choices=["llama3-8b", "llama3-70b"])
     args = ap.parse_args()
+    import torch.distributed as dist
     import swiftllm_b200
-    from swiftllm_b200.model_config import LLAMA3_8B
+    from swiftllm_b200.model_config import LLAMA3_8B, LLAMA3_70B
     from swiftllm_b200.worker.weight import synthetic_getter
-    cfg = dict(LLAMA3_8B)
+    cfg = dict(LLAMA3_8B if args.model == "llama3-8b" else LLAMA3_70B)
     if args.layers:
         cfg["num_hidden_layers"] = args.layers
     mc = swiftllm_b200.LlamaModelConfig(cfg)
-    dev = torch.device("cuda", 0)
-    torch.cuda.set_device(0)
+    n, rank, local = args.gpus, int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0"))
+    assert int(os.environ.get("WORLD_SIZE", "1")) == n, "launch with torchrun --nproc-per-node <--gpus>"
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(local)
+    if n > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
     Bd, S, bs = args.decodes, args.seqlen, 16
     bps = (max(S, args.prompt) + bs - 1) // bs + 2
     ec = swiftllm_b200.EngineConfig(model_path="", use_dummy=False, block_size=bs, gpu_mem_utilization=0.97, num_cpu_blocks=0,
                                     max_seqs_in_block_table=Bd + 1, max_blocks_per_seq=bps, max_batch_size=Bd + 1,
-                                    max_tokens_in_batch=args.chunk + Bd, dtype="bfloat16")
+                                    max_tokens_in_batch=args.chunk + Bd, dtype="bfloat16", tp_size=n, tp_rank=rank)
     with torch.inference_mode():
         m = swiftllm_b200.LlamaModel(ec, mc)
         m.load_weights(synthetic_getter(seed=0, std=0.02, device=dev))
@@ -65,24 +75,36 @@ def main():
                     m.forward(dec_ids, dec_sids, [S] * Bd)
             m.free_seqs_resources([0])
 
+        def barrier():
+            if n > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+
         def timed(piggyback):
             one_prompt(piggyback)
-            torch.cuda.synchronize()
+            barrier()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
             for _ in range(args.prompts):
                 one_prompt(piggyback)
-            e1.record(); torch.cuda.synchronize()
-            return e0.elapsed_time(e1) / (args.prompts * nchunks)
+            e1.record(); barrier()
+            ms = e0.elapsed_time(e1)
+            if n > 1:                                             # device time, max over ranks
+                t = torch.tensor([ms], device=dev); dist.all_reduce(t, op=dist.ReduceOp.MAX); ms = float(t.item())
+            return ms / (args.prompts * nchunks)
 
         m.forward(dec_ids, dec_sids, [S] * Bd)                    # allocate the decoding sequences' blocks once
         ms_pig, ms_sep = timed(True), timed(False)
     tok = args.chunk + Bd
-    print(json.dumps({"metric": "sarathi_step_tokens_per_s", "config": {"workload": f"llama3-8b bf16, {args.chunk}-token chunk of a "
-                      f"{args.prompt}-token prompt + {Bd} decodes at seq_len {S} per step (BASELINE.json configs[2])", "layers": cfg["num_hidden_layers"]},
+    if rank != 0:
+        torch.cuda.synchronize(); dist.barrier(); os._exit(0)
+    print(json.dumps({"metric": "sarathi_step_tokens_per_s", "config": {"workload": f"{args.model} bf16, {args.chunk}-token chunk of a "
+                      f"{args.prompt}-token prompt + {Bd} decodes at seq_len {S} per step (BASELINE.json configs[2] / [4])", "layers": cfg["num_hidden_layers"]},
                       "piggybacked": {"ms_per_step": ms_pig, "tokens_per_s": tok / (ms_pig * 1e-3)},
                       "separate_calls": {"ms_per_step": ms_sep, "tokens_per_s": tok / (ms_sep * 1e-3)},
-                      "steps_timed": args.prompts * nchunks, "data": "synthetic"}))
+                      "steps_timed": args.prompts * nchunks, "n_gpus": n, "parallelism": f"tp{n}", "data": "synthetic"}), flush=True)
+    if n > 1:
+        torch.cuda.synchronize(); dist.barrier(); os._exit(0)
 
 
 if __name__ == "__main__":
