@@ -203,3 +203,27 @@ def test_piggyback_planner_drives_the_product_to_the_whole_prompt_result():
             steps += 1
             assert steps < 40
         assert out == expect
+
+
+def test_oracle_prefix_attention_any_chunking_equals_whole_prompt_attention():
+    """Property (seeded random chunkings, ragged page boundaries, GQA): storing a prompt's K/V chunk by chunk and attending
+    through the block table gives, row for row, what causal attention over the packed prompt gives."""
+    rng = np.random.default_rng(123)
+    for trial in range(12):
+        nkv = int(rng.choice([1, 2, 4])); g = int(rng.choice([1, 2, 4])); nq = nkv * g
+        D = int(rng.choice([16, 32])); bs = int(rng.choice([4, 16])); Ltot = int(rng.integers(1, 70)); L = 2
+        q = torch.from_numpy(rng.standard_normal((Ltot, nq, D)).astype(np.float32)).half()
+        k = torch.from_numpy(rng.standard_normal((Ltot, nkv, D)).astype(np.float32)).half()
+        v = torch.from_numpy(rng.standard_normal((Ltot, nkv, D)).astype(np.float32)).half()
+        whole = K.prefill_attention_exact(q, k, v, [0], [Ltot], D ** -0.5)
+        nblk = (Ltot + bs - 1) // bs
+        perm = rng.permutation(nblk + 3)
+        bt = np.full((2, nblk + 1), -1, dtype=np.int32); bt[1, :nblk] = perm[:nblk]
+        kc = torch.full((nblk + 3, L, nkv, bs, D), float("nan"), dtype=torch.float16); vc = kc.clone()
+        pos = 0
+        while pos < Ltot:
+            n = int(rng.integers(1, Ltot - pos + 1))
+            K.store_kvcache_inplace(k[pos:pos + n], v[pos:pos + n], kc, vc, bt, [1], [0], [n], [], 1, n, bs, 1, prefill_prefix_lens=[pos])
+            out = K.prefix_prefill_attention_exact(q[pos:pos + n], kc, vc, bt, [1], [0], [n], [pos], D ** -0.5, bs, 1)
+            assert float((out - whole[pos:pos + n]).abs().max()) < 1e-12, (trial, pos, n)
+            pos += n
