@@ -6,6 +6,7 @@ set -u
 mkdir -p gpurun_out
 N=$(nvidia-smi -L | wc -l); echo "gpus: $N"
 export SLLM_RUN_PENDING=1
+# SLLM_DEBUG_SYNC=1 makes every native call synchronise and name itself when a kernel traps (use when a pending test fails)
 echo "== pending 1-GPU tests (chunked prefill: store, paged prefill attention gen1+gen2, model; fused rotary+store)"
 timeout 900 python -m pytest tests/test_chunked_prefill_gpu.py tests/test_decode_fusion_gpu.py tests/test_swap_device_gpu.py -m gpu -q -p no:cacheprovider --maxfail=8 > gpurun_out/pytest_pending_1gpu.log 2>&1; echo "rc=$?"; tail -15 gpurun_out/pytest_pending_1gpu.log | cut -c1-300
 echo "== validated suite still green"

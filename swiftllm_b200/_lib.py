@@ -73,12 +73,22 @@ def lib() -> ctypes.CDLL:
 LAUNCH_CALLS = 0
 
 
+# SLLM_DEBUG_SYNC=1: synchronise after every native call so that an asynchronous failure (a trapped kernel, an illegal
+# address) is reported at the call that caused it instead of at some later sync.  Debugging aid; never set in benchmarks.
+DEBUG_SYNC = os.environ.get("SLLM_DEBUG_SYNC", "0") == "1"
+
+
 def check(rc: int, what: str = ""):
     global LAUNCH_CALLS
     LAUNCH_CALLS += 1
     if rc != 0:
         msg = lib().sllm_last_error().decode("utf-8", "replace")
         raise RuntimeError(f"swiftllm_b200 native call failed{(' in ' + what) if what else ''}: {msg} (code {rc})")
+    if DEBUG_SYNC and not torch.cuda.is_current_stream_capturing():
+        try:
+            torch.cuda.synchronize()
+        except RuntimeError as e:
+            raise RuntimeError(f"swiftllm_b200: device-side failure detected right after `{what}`: {e}") from e
 
 
 def dtype_tag(dtype: torch.dtype) -> int:
