@@ -27,11 +27,16 @@ class _CudaToCpu(TorchFunctionMode):
             return args[0]
         if kwargs.get("pin_memory", False):
             kwargs["pin_memory"] = False
+        to_cuda = False
         if "device" in kwargs and _is_cuda_dev(kwargs["device"]):
-            kwargs["device"] = "cpu"
+            kwargs["device"] = "cpu"; to_cuda = True
         if any(_is_cuda_dev(a) for a in args):
-            args = tuple("cpu" if _is_cuda_dev(a) else a for a in args)
-        return func(*args, **kwargs)
+            args = tuple("cpu" if _is_cuda_dev(a) else a for a in args); to_cuda = True
+        out = func(*args, **kwargs)
+        # a host -> device transfer always yields a NEW tensor; `.to("cpu")` of a CPU tensor would alias its source
+        if to_cuda and getattr(func, "__name__", "") in ("to", "cuda") and args and out is args[0]:
+            out = out.clone()
+        return out
 
 
 # ---------------------------------------------------------------- oracle-backed stand-ins of the kernel wrappers
