@@ -123,7 +123,7 @@ __global__ void __launch_bounds__(512) allreduce_add_rmsnorm_kernel(const ArPara
 // partials), adds ITS residual row (the residual stays sharded by rows: only the owner ever needs it again), normalises, and
 // pushes the normalised row into every rank's x_out buffer (P2P stores).  Remote traffic per rank: 2 * (N-1)/N * T * H bytes,
 // 4x less than one-shot at N = 8.  Two barriers per exchange, both flag-based over peer memory:
-//   A  "my partial is complete"           (as above: published by CTA 0, awaited by every CTA)
+//   A  "my partial is complete"           (published by every CTA - idempotent -, awaited by every CTA)
 // With NVLS = true the N peer loads become ONE multimem.ld_reduce on the multicast address of the partial buffer (the NVSwitch
 // sums the N copies with fp32 accumulation) and the N peer stores ONE multimem.st on the multicast address of x_out.
 //   B  "my rows have landed everywhere"   published by the LAST CTA of a rank to finish (after a system fence), and awaited by
@@ -181,12 +181,11 @@ __global__ void __launch_bounds__(512) allreduce_add_rmsnorm_2shot_kernel(const 
     const int nvec = p.hidden >> 3;
     const uint32_t e = p.epoch[p.slot] + 1;
 
-    // ---- barrier A
+    // ---- barrier A.  EVERY CTA publishes (idempotent: the same epoch value; the partial is complete for all of them by stream
+    // order), so progress never depends on CTA 0 being dispatched before the CTAs that wait.
     if (threadIdx.x < p.nranks) {
-        if (blockIdx.x == 0) {
-            __threadfence_system();
-            st_release_sys(p.peer_flags[threadIdx.x] + p.slot * AR_MAX_RANKS + p.rank, e);
-        }
+        __threadfence_system();
+        st_release_sys(p.peer_flags[threadIdx.x] + p.slot * AR_MAX_RANKS + p.rank, e);
         const uint32_t* mine = p.peer_flags[p.rank] + p.slot * AR_MAX_RANKS + threadIdx.x;
         uint32_t spins = 0;
         while ((int32_t)(ld_acquire_sys(mine) - e) < 0) {
