@@ -39,6 +39,12 @@ def kernels():
     return out
 
 
+def norm(body):
+    """Instruction stream with the offsets into constant bank 4 (module-level constants: printf format strings, globals)
+    blanked: adding an unrelated kernel with its own strings to a translation unit shifts them."""
+    return [re.sub(r"c\[0x4\]\[0x[0-9a-f]+\]", "c[0x4][*]", i) for i in body]
+
+
 def demangle(names):
     r = subprocess.run(["cu++filt"] + list(names), capture_output=True, text=True).stdout.splitlines()
     return dict(zip(names, r))
@@ -60,12 +66,16 @@ def main():
         if n in ks:
             if ks[n] == base[n]:
                 same += 1
+            elif norm(ks[n]) == norm(base[n]):
+                same += 1
+                print(f"same*    {dm[n]}  (identical up to constant-bank-4 offsets, i.e. addresses of printf strings / globals)")
             else:
                 changed += 1
-                print(f"CHANGED  {dm[n]}  ({len(base[n])} -> {len(ks[n])} instructions)")
+                d = sum(1 for x, y in zip(ks[n], base[n]) if x != y) + abs(len(ks[n]) - len(base[n]))
+                print(f"CHANGED  {dm[n]}  ({len(base[n])} -> {len(ks[n])} instructions, {d} differ)")
         else:
             # a template parameter may have been appended: match on identical instruction streams
-            twins = [m for m in ks if m not in base and ks[m] == base[n]]
+            twins = [m for m in ks if m not in base and norm(ks[m]) == norm(base[n])]
             if twins:
                 same += 1
                 print(f"renamed  {dm[n]}  ->  {dm[twins[0]]}  (identical instructions)")

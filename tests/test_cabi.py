@@ -93,3 +93,29 @@ def test_no_silent_fallback_without_cuda():
     x = torch.zeros(2, 64, dtype=torch.float16)
     with pytest.raises(RuntimeError, match="no CPU path"):
         rmsnorm_inplace(x, torch.ones(64, dtype=torch.float16), 1e-5)
+
+
+def test_validated_kernels_still_have_their_validated_instruction_streams():
+    """profiles/r1_validated_kernels.json holds a hash of the (normalised) SASS of every kernel as it last ran `pytest -m gpu`,
+    smoke() and bench.py on a B200.  Refactoring a kernel's source without a GPU at hand (templates, shared headers) is only safe
+    if the instruction stream it compiles to is unchanged - or the change was reviewed and listed under "equivalent".  A kernel that
+    no longer matches must be re-validated on a GPU and the manifest regenerated (scripts/sass_diff.py)."""
+    import hashlib
+    import importlib.util
+    import json
+    import shutil
+    import subprocess
+    import pytest
+    if shutil.which("cuobjdump") is None or shutil.which("nvcc") is None:
+        pytest.skip("CUDA toolkit not on PATH")
+    man = json.load(open(os.path.join(ROOT, "profiles", "r1_validated_kernels.json")))
+    nvcc = subprocess.run(["nvcc", "--version"], capture_output=True, text=True).stdout
+    if man["nvcc"] not in nvcc:
+        pytest.skip("different nvcc than the one the manifest was made with")
+    spec = importlib.util.spec_from_file_location("sass_diff", os.path.join(ROOT, "scripts", "sass_diff.py"))
+    sd = importlib.util.module_from_spec(spec); spec.loader.exec_module(sd)
+    have = {hashlib.sha256("\n".join(sd.norm(body)).encode()).hexdigest() for body in sd.kernels().values()}
+    assert have, "no objects under swiftllm_b200/csrc/build: run python -m swiftllm_b200.build"
+    changed = [name for name, k in man["kernels"].items()
+               if k["sha256"] not in have and man["equivalent"].get(name, {}).get("sha256") not in have]
+    assert not changed, f"validated kernels whose SASS changed (re-validate on a GPU): {changed}"
