@@ -111,8 +111,10 @@ def test_prefill_attention_paged_vs_exact_oracle(dtype, geom, prefill_gen):
 
 @pytest.mark.parametrize("dtype", DTYPES)
 def test_prefill_attention_paged_nan_in_unowned_pages_is_harmless(dtype, prefill_gen):
-    """Pages past the end of a sequence and slots past its last token may hold anything (other sequences' data, NaN): the tail
-    mask must keep them out of both S and P.V."""
+    """Blocks the sequence does not own may hold anything (NaN here): they are never loaded.  Slots of the LAST owned page past the
+    sequence end are loaded by the TMA kernel (whole pages): their K may be NaN (the tail mask is a select), their V is multiplied by
+    P = 0 exactly, so it must be finite - as it always is in a cache that is zero-initialised and only receives finite K/V - but may
+    be huge (3e4 here).  tests/test_kernel_logic_mirror_cpu.py holds the same contract on CPU."""
     nq, nkv, D, bs, L = 8, 2, 128, 16, 1
     prefix, chunk = [70], [21]                                 # kv length 91: last page holds 11 valid slots
     g = torch.Generator().manual_seed(9)
@@ -121,7 +123,7 @@ def test_prefill_attention_paged_nan_in_unowned_pages_is_harmless(dtype, prefill
     kc = torch.randn(nblk, L, nkv, bs, D, generator=g).to(dtype); vc = torch.randn(nblk, L, nkv, bs, D, generator=g).to(dtype)
     o64 = K.prefix_prefill_attention_exact(q, kc, vc, bt.numpy(), sids, [0], chunk, prefix, D ** -0.5, bs, 0)
     last = int(bt[sids[0], 5])
-    kc[last, :, :, 11:] = float("nan"); vc[last, :, :, 11:] = float("nan")
+    kc[last, :, :, 11:] = float("nan"); vc[last, :, :, 11:] = 3.0e4
     owned = set(bt[sids[0], :6].tolist())
     for b in range(nblk):
         if b not in owned:
