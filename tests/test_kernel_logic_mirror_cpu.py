@@ -173,3 +173,67 @@ def test_mirror_of_the_mma_sync_paged_prefill_kernel_matches_the_definition(seed
     got = mirror_mma(q, kc, vc, bt, sids, starts, chunk, prefix, 32 ** -0.5, 1, bs)
     assert np.isfinite(got).all()
     assert np.abs(got - ref).max() < 1e-9
+
+
+# ----------------------------------------------------------------------------- store_kv_prefill_kernel<T, PREFIX = true>
+def mirror_store_prefix(k, kc, bt, sids, starts, chunk, prefix, layer, bs):
+    """csrc/kvcache.cu: grid (cdiv(max_chunk, bs) + 1, num_seqs); CTA (x, b) fills page prefix_b / bs + x of sequence b with the
+    chunk tokens that fall into it.  Returns how often every cache element was written."""
+    nkv, D = k.shape[1], k.shape[2]
+    hits = np.zeros(kc.shape, dtype=np.int32)
+    for b in range(len(chunk)):
+        for x in range((max(chunk) + bs - 1) // bs + 1):
+            pre, ln = prefix[b], chunk[b]
+            pb = x + pre // bs
+            lo, hi = max(pb * bs, pre), min(pb * bs + bs, pre + ln)
+            if lo >= hi:
+                continue
+            off0, ntok, row0 = lo - pb * bs, hi - lo, starts[b] + (lo - pre)
+            blk = int(bt[sids[b], pb])
+            for i in range(ntok * nkv * (D // 8)):                  # the thread loop (order irrelevant)
+                c, h, t = i % (D // 8), (i // (D // 8)) % nkv, i // ((D // 8) * nkv)
+                kc[blk, layer, h, off0 + t, 8 * c:8 * c + 8] = k[row0 + t, h, 8 * c:8 * c + 8]
+                hits[blk, layer, h, off0 + t, 8 * c:8 * c + 8] += 1
+    return hits
+
+
+@pytest.mark.parametrize("bs", [4, 16])
+def test_mirror_of_the_prefix_store_kernel_writes_every_slot_exactly_once(bs):
+    rng = np.random.default_rng(bs)
+    for _ in range(5):
+        n = 4
+        prefix = [int(rng.integers(0, 60)) for _ in range(n)]
+        chunk = [int(rng.integers(1, 50)) for _ in range(n)]
+        need = [(p + c + bs - 1) // bs for p, c in zip(prefix, chunk)]
+        perm = rng.permutation(sum(need) + 1)
+        bt = np.full((n, max(need) + 1), -1, dtype=np.int32); p0 = 0
+        for s, m in enumerate(need):
+            bt[s, :m] = perm[p0:p0 + m]; p0 += m
+        starts = list(np.cumsum([0] + chunk[:-1]))
+        k = torch.from_numpy(rng.standard_normal((sum(chunk), 2, 16)).astype(np.float32)).half()
+        kc = torch.zeros(sum(need) + 1, 2, 2, bs, 16, dtype=torch.float16)
+        ko, vo = torch.zeros_like(kc), torch.zeros_like(kc)
+        hits = mirror_store_prefix(k, kc, bt, list(range(n)), starts, chunk, prefix, 1, bs)
+        K.store_kvcache_inplace(k, k, ko, vo, bt, list(range(n)), starts, chunk, [], n, sum(chunk), bs, 1, prefill_prefix_lens=prefix)
+        assert torch.equal(kc, ko)
+        assert hits.max() == 1 and hits.sum() == sum(chunk) * 2 * 16          # every (token, head, d) written exactly once
+
+
+# ----------------------------------------------------------------------------- swap_blocks_gather_kernel
+def test_mirror_of_the_swap_gather_kernel_covers_every_vector_exactly_once():
+    """csrc/swap_gather.cu: grid (n, SW_SPLIT = 8), 256 threads, two 16-byte vectors per thread and iteration."""
+    SPLIT, THREADS = 8, 256
+    for block_vecs in (1, 7, 255, 256, 257, 4096, 65536, 65536 + 13):
+        hits = np.zeros(block_vecs, dtype=np.int32)
+        per = (block_vecs + SPLIT - 1) // SPLIT
+        for y in range(SPLIT):
+            lo, hi = y * per, min(block_vecs, y * per + per)
+            for tid in range(THREADS):
+                i = lo + tid
+                while i < hi:
+                    hits[i] += 1
+                    j = i + THREADS
+                    if j < hi:
+                        hits[j] += 1
+                    i += 2 * THREADS
+        assert (hits == 1).all(), block_vecs
