@@ -1,5 +1,9 @@
-"""Per-forward metadata handed to every kernel wrapper.  Same fields as the reference dataclass
-(swiftllm/worker/infer_state.py:5-29); the trailing optional fields are additions of this implementation."""
+"""Per-forward metadata handed to every kernel wrapper.
+
+The field NAMES are the interface the reference's wrappers read (`swiftllm/worker/infer_state.py:5-29`: anything that is
+called with an `infer_state` looks these attributes up), so they are kept; grouping, types and the trailing optional fields
+are this implementation's.  All tensors are int32 (or the model dtype for cos/sin) on the model's device; instances are always
+built with keyword arguments (worker/model.py)."""
 import dataclasses
 from typing import Optional
 
@@ -8,39 +12,40 @@ import torch
 
 @dataclasses.dataclass
 class LlamaInferState:
-    batch_size: int
-    num_tokens: int
-
-    seq_ids: torch.Tensor   # [batch_size]
-    softmax_scale: float    # Equal to 1/sqrt(head_dim)
-
+    # ---- the packed batch: prefill sequences first, then one row per decoding sequence
+    batch_size: int                                 # sequences in the batch
+    num_tokens: int                                 # rows of the activation matrix
+    seq_ids: torch.Tensor                           # [batch_size] block-table row of every sequence
     num_prefill_seqs: int
-    num_prefill_tokens: int
-    prefill_seq_start_locs: torch.Tensor  # [num_prefill_seqs]
-    prefill_seq_start_locs_with_end: torch.Tensor  # [num_prefill_seqs+1]
-    prefill_seq_lens: torch.Tensor  # [num_prefill_seqs]
+    num_decoding_seqs: int
+    num_prefill_tokens: int                         # rows [0, num_prefill_tokens) are prompt tokens
+
+    # ---- prefill part
+    prefill_seq_lens: torch.Tensor                  # [num_prefill_seqs] tokens of each prompt (chunk) in this batch
+    prefill_seq_start_locs: torch.Tensor            # [num_prefill_seqs] first row of each prompt
+    prefill_seq_start_locs_with_end: torch.Tensor   # [num_prefill_seqs + 1] the same, closed with num_prefill_tokens
     max_prefill_len: int
 
-    num_decoding_seqs: int
-    decoding_seq_lens: torch.Tensor  # [num_decoding_seqs]
+    # ---- decode part
+    decoding_seq_lens: torch.Tensor                 # [num_decoding_seqs] sequence lengths INCLUDING the new token
     max_decoding_len: int
+    seq_block_size: int                             # the reference's flash-decoding split (model.py:305-324) ...
+    num_seq_blocks: int                             # ... and the number of splits of the longest sequence
 
-    seq_block_size: int
-    num_seq_blocks: int
+    # ---- attention / rotary constants of the step
+    softmax_scale: float                            # head_dim ** -0.5
+    position_cos: torch.Tensor                      # [num_tokens, head_dim / 2] rows of the RoPE tables at the tokens' positions
+    position_sin: torch.Tensor
 
-    position_cos: torch.Tensor  # [num_tokens, head_dim//2]
-    position_sin: torch.Tensor  # [num_tokens, head_dim//2]
+    ignore_kvcache: bool                            # memory-profiling forward: no KV store, no decode attention
 
-    ignore_kvcache: bool    # Skip storing the key/value cache, useful when profiling the number of kv blocks
-
-    # ---- additions (not in the reference) ----
-    # seq_block_size the library should use for paged attention: 0 = choose v1/v2 automatically.  The
-    # reference's `seq_block_size` above is still computed with its heuristic (model.py:320-324) and can be
-    # forced onto the kernel by setting this field to it.
+    # ---- additions of this implementation (defaults keep the reference's behaviour)
+    # Split size the library should use for paged attention; 0 = choose v1 / v2 itself.  `seq_block_size` above can be forced
+    # onto the kernel by copying it here.
     paged_attn_seq_block_size: int = 0
-    last_token_indices: Optional[torch.Tensor] = None   # [batch_size] (post_layer.py:24-31), precomputed on the host
+    last_token_indices: Optional[torch.Tensor] = None   # [batch_size] rows to sample from (post_layer.py:24-31), host-computed
     # Chunked ("prefix-aware") prefill, SURVEY.md §8 f-1: prefill entry i holds the tokens at positions
-    # [prefill_prefix_lens[i], prefill_prefix_lens[i] + prefill_seq_lens[i]) of its sequence; everything before is
-    # already in the KV cache.  None = the reference's contract (whole prompts, attention over the packed k/v).
-    prefill_prefix_lens: Optional[torch.Tensor] = None  # [num_prefill_seqs] int32
+    # [prefill_prefix_lens[i], prefill_prefix_lens[i] + prefill_seq_lens[i]) of its sequence; everything before is already in
+    # the KV cache.  None = whole prompts, attention over the packed k/v.
+    prefill_prefix_lens: Optional[torch.Tensor] = None  # [num_prefill_seqs]
     max_prefill_kv_len: int = 0                          # max_i(prefix_i + chunk_i); 0 when not chunked
