@@ -119,3 +119,31 @@ def test_validated_kernels_still_have_their_validated_instruction_streams():
     changed = [name for name, k in man["kernels"].items()
                if k["sha256"] not in have and man["equivalent"].get(name, {}).get("sha256") not in have]
     assert not changed, f"validated kernels whose SASS changed (re-validate on a GPU): {changed}"
+
+
+def test_product_never_imports_the_oracle_or_reads_the_reference():
+    """The oracle is test infrastructure: only tests/, __graft_entry__.smoke() and bench.py's CPU arms may import it; nothing that
+    ships may read /root/reference or baseline/_ref (scripts/ref_triton_bench.py and install_reference.sh exist FOR the reference)."""
+    offenders = []
+    for base in ("swiftllm_b200", "examples"):
+        for d, _, files in os.walk(os.path.join(ROOT, base)):
+            for f in files:
+                if not f.endswith((".py", ".cu", ".cuh", ".h")):
+                    continue
+                txt = open(os.path.join(d, f), encoding="utf-8").read()
+                if re.search(r"^\s*(from|import)\s+oracle\b", txt, flags=re.M) or "/root/reference" in txt or "baseline/_ref" in txt:
+                    offenders.append(os.path.relpath(os.path.join(d, f), ROOT))
+    assert not offenders, offenders
+    # bench.py: the oracle is imported in exactly one place, the CPU arm (cpu_baseline / --impl reference)
+    import ast
+    src = open(os.path.join(ROOT, "bench.py"), encoding="utf-8").read()
+    assert "/root/reference" not in src
+    where = set()
+    for fn in ast.walk(ast.parse(src)):
+        if isinstance(fn, ast.FunctionDef):
+            for node in ast.walk(fn):
+                if isinstance(node, ast.ImportFrom) and (node.module or "").split(".")[0] == "oracle":
+                    where.add(fn.name)
+                if isinstance(node, ast.Import) and any(a.name.split(".")[0] == "oracle" for a in node.names):
+                    where.add(fn.name)
+    assert where == {"cpu_decode_sample"}, where
