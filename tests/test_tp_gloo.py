@@ -184,3 +184,61 @@ def _worker_model_w(rank, world, port, ret, comm):
     if world == 3:                                         # heads / FFN columns must divide by the world size
         CFG = dict(CFG, num_attention_heads=6, num_key_value_heads=3, hidden_size=96, intermediate_size=192)
     _worker_model(rank, world, port, ret, False, comm)
+
+
+def _worker_chunked(rank, world, port, ret):
+    """Chunked prefill + piggybacked decode through the PRODUCT model with tp_size=world on CPU (oracle-backed kernels, gloo
+    collectives, vocabulary-sharded lm_head) against the unsharded oracle run with whole prompts."""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import warnings
+    import numpy as np
+    import swiftllm_b200
+    from cpu_shim import product_on_cpu
+    from oracle.model import OracleLlama, OracleWeights
+    from swiftllm_b200.worker.weight import dict_getter
+    from test_host_path_cpu import _hf_tensors
+    cfg = dict(CFG, num_hidden_layers=2, vocab_size=96)
+    w = OracleWeights.random(cfg, dtype=torch.float16, seed=14, std=0.08)
+    ok = True
+    with product_on_cpu(), warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        ec = swiftllm_b200.EngineConfig(model_path="", use_dummy=False, block_size=16, gpu_mem_utilization=0.9, num_cpu_blocks=2,
+                                        max_seqs_in_block_table=8, max_blocks_per_seq=8, max_batch_size=8, max_tokens_in_batch=128,
+                                        dtype="float16", tp_size=world, tp_rank=rank, shard_lm_head=True)
+        m = swiftllm_b200.LlamaModel(ec, swiftllm_b200.LlamaModelConfig(cfg))
+        m.load_weights(dict_getter(_hf_tensors(w, cfg["intermediate_size"])))
+        m.init_kvcache_and_swap(20)
+        o = OracleLlama(cfg, w, block_size=16, num_blocks=20, num_cpu_blocks=2, max_seqs_in_block_table=8, max_blocks_per_seq=8,
+                        attn="exact", dtype=torch.float16)
+        rng = np.random.default_rng(8)
+        pa, pb = rng.integers(0, 96, size=37).tolist(), rng.integers(0, 96, size=6).tolist()
+        tb = m.forward([pb], [4], [])                                                   # B: whole prompt
+        ok &= tb == o.forward([pb], [4], [])
+        m.forward([pa[:16], tb], [1, 4], [7], prefill_prefix_lens_list=[0])            # A chunk 1 + decode of B
+        tb2 = o.forward([tb], [4], [7])
+        t = m.forward([pa[16:29], tb2], [1, 4], [8], prefill_prefix_lens_list=[16])    # A chunk 2 (enters a page mid-way)
+        tb3 = o.forward([tb2], [4], [8])
+        ok &= t[1] == tb3[0]
+        t = m.forward([pa[29:]], [1], [], prefill_prefix_lens_list=[29])               # A last chunk
+        ok &= t == o.forward([pa], [1], [])                                             # == whole-prompt prefill of A
+    gathered = [None] * world
+    dist.all_gather_object(gathered, bool(ok))
+    if rank == 0:
+        ret.put(gathered)
+    dist.destroy_process_group()
+
+
+def test_product_model_chunked_prefill_under_tensor_parallelism_on_cpu():
+    ctx = mp.get_context("spawn")
+    ret = ctx.Queue()
+    procs = [ctx.Process(target=_worker_chunked, args=(r, 2, 29755, ret)) for r in range(2)]
+    for p in procs:
+        p.start()
+    oks = ret.get(timeout=240)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert all(oks), oks
