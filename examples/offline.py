@@ -20,6 +20,36 @@ import torch  # noqa: E402
 import swiftllm_b200  # noqa: E402
 
 
+def generate(model, input_ids, new_tokens: int, chunk: int = 0):
+    """Greedy generation for a batch of prompts (sequence i uses block-table row i).  chunk > 0: the prompts are prefilled
+    `chunk` tokens at a time through the paged cache.  Returns (token lists, prefill seconds, decode seconds)."""
+    seq_ids = list(range(len(input_ids)))
+    t0 = time.perf_counter()
+    if chunk > 0:                      # every call carries the next chunk of each unfinished prompt
+        done = [0] * len(input_ids)
+        last = [None] * len(input_ids)
+        while any(d < len(p) for d, p in zip(done, input_ids)):
+            live = [i for i in seq_ids if done[i] < len(input_ids[i])]
+            toks = model.forward([input_ids[i][done[i]:done[i] + chunk] for i in live], live, [],
+                                 prefill_prefix_lens_list=[done[i] for i in live])
+            for i, t in zip(live, toks):
+                done[i] = min(len(input_ids[i]), done[i] + chunk)
+                if done[i] == len(input_ids[i]):
+                    last[i] = t             # the token sampled after the LAST chunk is the first generated token
+    else:
+        last = model.forward(input_ids, seq_ids, [])
+    t_prefill = time.perf_counter() - t0
+    outputs = [[t] for t in last]
+    seq_lens = [len(p) for p in input_ids]
+    t0 = time.perf_counter()
+    for _ in range(new_tokens - 1):
+        seq_lens = [n + 1 for n in seq_lens]
+        last = model.forward([[t] for t in last], seq_ids, seq_lens)
+        for o, t in zip(outputs, last):
+            o.append(t)
+    return outputs, t_prefill, time.perf_counter() - t0
+
+
 def main():
     ap = argparse.ArgumentParser(description=__doc__, formatter_class=argparse.RawDescriptionHelpFormatter)
     src = ap.add_mutually_exclusive_group(required=True)
@@ -57,32 +87,8 @@ def main():
     model.init_kvcache_and_swap(num_blocks)
     print(f"{num_blocks} KV blocks; model ready in {time.perf_counter() - t0:.1f} s")
 
+    outputs, t_prefill, t_decode = generate(model, input_ids, args.new_tokens, args.chunk)
     seq_ids = list(range(len(input_ids)))
-    t0 = time.perf_counter()
-    if args.chunk > 0:                 # every call carries the next chunk of each unfinished prompt
-        done = [0] * len(input_ids)
-        first = [None] * len(input_ids)
-        while any(d < len(p) for d, p in zip(done, input_ids)):
-            live = [i for i in seq_ids if done[i] < len(input_ids[i])]
-            toks = model.forward([input_ids[i][done[i]:done[i] + args.chunk] for i in live], live, [],
-                                 prefill_prefix_lens_list=[done[i] for i in live])
-            for i, t in zip(live, toks):
-                done[i] = min(len(input_ids[i]), done[i] + args.chunk)
-                if done[i] == len(input_ids[i]):
-                    first[i] = t            # the token sampled after the LAST chunk is the first generated token
-        last = first
-    else:
-        last = model.forward(input_ids, seq_ids, [])
-    t_prefill = time.perf_counter() - t0
-    outputs = [[t] for t in last]
-    seq_lens = [len(p) for p in input_ids]
-    t0 = time.perf_counter()
-    for _ in range(args.new_tokens - 1):
-        seq_lens = [n + 1 for n in seq_lens]
-        last = model.forward([[t] for t in last], seq_ids, seq_lens)
-        for o, t in zip(outputs, last):
-            o.append(t)
-    t_decode = time.perf_counter() - t0
     for p, o in zip(input_ids, outputs):
         print(f"[{len(p)} prompt tokens] -> {show(o)}")
     print(f"prefill {t_prefill * 1e3:.1f} ms ({sum(map(len, input_ids)) / t_prefill:.0f} tok/s), "

@@ -227,3 +227,20 @@ def test_oracle_prefix_attention_any_chunking_equals_whole_prompt_attention():
             out = K.prefix_prefill_attention_exact(q[pos:pos + n], kc, vc, bt, [1], [0], [n], [pos], D ** -0.5, bs, 1)
             assert float((out - whole[pos:pos + n]).abs().max()) < 1e-12, (trial, pos, n)
             pos += n
+
+
+def test_offline_example_generation_loop_chunked_equals_unchunked():
+    """examples/offline.py: generate() with --chunk must produce the tokens of whole-prompt prefill (product on CPU)."""
+    import importlib.util
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("offline_example", os.path.join(root, "examples", "offline.py"))
+    ex = importlib.util.module_from_spec(spec); spec.loader.exec_module(ex)
+    w = OracleWeights.random(CFG, dtype=torch.float16, seed=5, std=0.08)
+    rng = np.random.default_rng(3)
+    prompts = [rng.integers(0, 300, size=n).tolist() for n in (9, 40, 1, 23)]
+    with product_on_cpu():
+        a, _, _ = ex.generate(_product(w), prompts, 5, chunk=0)
+        b, _, _ = ex.generate(_product(w), prompts, 5, chunk=16)
+        c, _, _ = ex.generate(_product(w), prompts, 5, chunk=7)
+    assert a == b == c and all(len(o) == 5 for o in a)
