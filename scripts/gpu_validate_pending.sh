@@ -28,7 +28,7 @@ except Exception as e: print('  no line', e)"
 done
 if [ "$N" -ge 2 ]; then
   echo "== NVLink probe (flag round trip, peer read / write bandwidth)"
-  [ -x probes/build/p2p_latency ] || nvcc -gencode arch=compute_100a,code=sm_100a -O2 -std=c++17 -o probes/build/p2p_latency probes/p2p_latency.cu
+  mkdir -p probes/build; [ -x probes/build/p2p_latency ] || nvcc -gencode arch=compute_100a,code=sm_100a -O2 -std=c++17 -o probes/build/p2p_latency probes/p2p_latency.cu
   timeout 120 probes/build/p2p_latency > gpurun_out/p2p_latency.log 2>&1; echo "rc=$?"; cat gpurun_out/p2p_latency.log
   echo "== pending TP tests (two-shot exchange, vocab-sharded lm_head)"
   timeout 900 python -m pytest tests/test_tp_gpu.py -m gpu -q -p no:cacheprovider --maxfail=4 > gpurun_out/pytest_pending_tp.log 2>&1; echo "rc=$?"; tail -8 gpurun_out/pytest_pending_tp.log | cut -c1-300
