@@ -254,6 +254,9 @@ class LlamaModel:
             assert len(prefix_lens) == num_prefill_seqs and min(prefix_lens) >= 0, \
                 "prefill_prefix_lens_list needs one non-negative entry per prefill sequence"
             assert not ignore_kvcache, "chunked prefill reads the KV cache: ignore_kvcache is not applicable"
+            # first chunks only (every prefix 0): nothing to read back from the cache, so this IS the reference's whole-prompt
+            # contract - packed-k/v attention and the plain store
+            chunked = max(prefix_lens) > 0
         else:
             prefix_lens = [0] * num_prefill_seqs
         seq_lengths_list = [p + n for p, n in zip(prefix_lens, prefill_lens)] + list(decoding_seq_lens_list)
