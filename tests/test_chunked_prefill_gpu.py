@@ -178,7 +178,7 @@ def test_prefill_attention_paged_sarathi_shape_property(prefill_gen):
             max_decoding_len=4096, paged_attn_seq_block_size=0)
     od = torch.zeros(1, nq * D, dtype=dtype, device=DEV)
     paged_attention(q[-1:].to(DEV), kc.to(DEV), vc.to(DEV), bt.to(DEV), None, NS(block_size=bs), st, 0, od)
-    assert (od.cpu().float() - o[-1].reshape(1, -1).float()).abs().max() <= 2 ** -6 * float(o[-1].float().abs().max())
+    assert (od.cpu().float() - o[-1].reshape(1, -1).float()).abs().max() <= 2 ** -5 * float(o[-1].float().abs().max())   # two bf16 kernels, each within 8e-3 of fp64
 
 
 # ----------------------------------------------------------------------------- model level
