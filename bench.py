@@ -30,6 +30,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
+import numpy as np  # noqa: E402
 import torch  # noqa: E402
 
 METRIC = "decode_tokens_per_s"
@@ -60,6 +61,13 @@ def parse():
     ap.add_argument("--fuse-rotary-store", action="store_true",
                     help="decode: rotary + KV store in one launch per layer (opt-in A/B)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-ref-triton", action="store_true",
+                    help="skip timing the unmodified reference's Triton path (baseline/_ref/src) on this GPU (N = 1 only)")
+    ap.add_argument("--ref-triton-dtypes", type=str, default="fp16,bf16",
+                    help="reference Triton arm: fp16 = the tree as shipped, bf16 = its fp16 literals patched in a temp copy")
+    ap.add_argument("--no-parity", action="store_true", help="skip the oracle parity check at the benchmarked shape")
+    ap.add_argument("--parity-seqs", type=int, default=2, help="sequences re-run through the CPU oracle (tokens + logits)")
+    ap.add_argument("--no-live-traffic", action="store_true", help="skip the ncu DRAM-byte measurement of the decode kernel")
     ap.add_argument("--no-prefill", action="store_true")
     ap.add_argument("--cpu-sample-seqs", type=int, default=8)
     ap.add_argument("--profile-range", type=int, default=0,
@@ -196,6 +204,166 @@ def workload_config(args, cfg, n):
             "parallelism": f"tp{n}", "l2": "inputs larger than L2 (KV working set and weights >> 126 MB)"}
 
 
+
+# --------------------------------------------------------------------------- reference Triton arm (north_star: "next to the
+# reference's own Triton path on one B200"): the UNMODIFIED reference under baseline/_ref/src, in its own process
+def run_reference_triton(args, dtypes):
+    """Runs scripts/ref_triton_bench.py once per dtype BEFORE this process allocates its own 143 GB (both need most of the
+    GPU).  Same workload, same public call (LlamaModel.forward: host lists in, host ints out), same step count and
+    warm-up, CUDA events around the K steps.  Returns {dtype: json-line-or-error}."""
+    out = {}
+    script = os.path.join(ROOT, "scripts", "ref_triton_bench.py")
+    for dt in dtypes:
+        env = dict(os.environ, REF_DTYPE=dt, REF_BATCH=str(args.batch), REF_SEQLEN=str(args.seqlen),
+                   REF_STEPS=str(args.steps), REF_WARMUP=str(max(args.warmup, 3)), CUDA_VISIBLE_DEVICES=os.environ.get("CUDA_VISIBLE_DEVICES", "0"))
+        t0 = time.perf_counter()
+        try:
+            r = subprocess.run([sys.executable, script], env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=900)
+            lines = [l for l in r.stdout.strip().splitlines() if l.startswith("{")]
+            if r.returncode == 0 and lines:
+                d = json.loads(lines[-1])
+            else:
+                d = {"error": f"rc={r.returncode}: " + (r.stderr.strip().splitlines()[-1][:300] if r.stderr.strip() else "no output")}
+        except Exception as e:  # noqa: BLE001
+            d = {"error": str(e)[:300]}
+        d["wall_s"] = round(time.perf_counter() - t0, 1)
+        out[dt] = d
+    return out
+
+
+# --------------------------------------------------------------------------- live DRAM traffic of the decode kernel (ncu)
+def measure_traffic_live(args, mc, n):
+    """dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the paged-decode kernel at this run's geometry
+    (scripts/paged_attn_traffic.py under ncu, second launch).  Returns (bytes, source) or (None, reason)."""
+    import shutil
+    ncu = shutil.which("ncu") or "/usr/local/cuda/bin/ncu"
+    if not os.path.exists(ncu):
+        return None, "ncu not found"
+    cmd = [ncu, "--metrics", "dram__bytes_read.sum,dram__bytes_write.sum", "--clock-control", "none", "--csv",
+           "-k", "regex:paged_attn(_tc)?_kernel", "--launch-skip", "1", "--launch-count", "1",
+           sys.executable, os.path.join(ROOT, "scripts", "paged_attn_traffic.py"), "--batch", str(args.batch),
+           "--seqlen", str(args.seqlen), "--nq", str(mc.num_q_heads // n), "--nkv", str(mc.num_kv_heads // n),
+           "--head-dim", str(mc.head_dim)]
+    try:
+        r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=300,
+                           env=dict(os.environ, SLLM_PAGED_ATTN_GEN=os.environ.get("SLLM_PAGED_ATTN_GEN", "")))
+    except Exception as e:  # noqa: BLE001
+        return None, f"ncu failed: {str(e)[:120]}"
+    import csv, io
+    rows = [l for l in r.stdout.splitlines() if l.startswith('"')]
+    vals = {}
+    kern = None
+    for row in csv.DictReader(io.StringIO("\n".join(rows))):
+        try:
+            vals[row["Metric Name"]] = float(row["Metric Value"].replace(",", ""))
+            kern = row.get("Kernel Name", kern)
+        except (KeyError, ValueError):
+            continue
+    if "dram__bytes_read.sum" not in vals or "dram__bytes_write.sum" not in vals:
+        tail = (r.stdout.strip().splitlines() or r.stderr.strip().splitlines() or ["no output"])[-1][:160]
+        return None, f"ncu produced no dram__bytes (rc={r.returncode}): {tail}"
+    return vals["dram__bytes_read.sum"] + vals["dram__bytes_write.sum"], \
+        (f"live: ncu dram__bytes_read.sum ({vals['dram__bytes_read.sum']:.0f}) + dram__bytes_write.sum ({vals['dram__bytes_write.sum']:.0f}) "
+         f"of one launch of {kern} at this geometry (scripts/paged_attn_traffic.py, 1-layer cache, scattered pages)")
+
+
+# --------------------------------------------------------------------------- parity at the benchmarked shape (oracle = checker)
+def parity_check(model, mc, ids, sids, lens, n_rows=8, n_seqs=2):
+    """Outside every timed region, TP = 1.  (a) n_rows sampled (sequence, kv head) GQA groups of the paged-decode kernel's
+    output at the benchmarked batch x seq_len, in three layers, against oracle.kernels.paged_attention_exact (fp64) on the
+    pages of exactly those sequences; (b) n_seqs whole sequences re-run through the CPU oracle (oracle.model.OracleLlama,
+    fp64 attention, this model's weights and this cache's pages): sampled token and logits.  Raises AssertionError on mismatch."""
+    from oracle import kernels as K
+    from oracle.model import OracleLlama, OracleWeights
+    from swiftllm_b200.worker.layers import transformer_layer as TL
+    B, bs, D, nkv, nq, L = len(sids), 16, mc.head_dim, mc.num_kv_heads, mc.num_q_heads, mc.num_layers
+    g = nq // nkv
+    rng = torch.Generator().manual_seed(99)
+    layers = sorted({0, L // 2, L - 1})
+    picks = [(int(torch.randint(0, B, (1,), generator=rng)), int(torch.randint(0, nkv, (1,), generator=rng))) for _ in range(n_rows)]
+    cap = {}
+    orig = TL.paged_attention
+
+    def hooked(q, k_cache, v_cache, block_table, mcfg, ecfg, st, cur_layer, o):
+        orig(q, k_cache, v_cache, block_table, mcfg, ecfg, st, cur_layer, o)
+        if cur_layer in layers:
+            cap[cur_layer] = (q.detach().clone(), o.detach().clone())
+    was_graph = model.engine_config.use_cuda_graph
+    model.engine_config.use_cuda_graph = False
+    model.post_layer.keep_logits = True
+    TL.paged_attention = hooked
+    try:
+        toks = model.forward(ids, sids, lens)
+    finally:
+        TL.paged_attention = orig
+        model.engine_config.use_cuda_graph = was_graph
+    logits = model.post_layer.last_logits.float().cpu()
+    model.post_layer.keep_logits = False; model.post_layer.last_logits = None
+    bt = model.gpu_block_manager.block_table
+    res = {"attention_rows": [], "sequences": []}
+    worst = 0.0
+    for li in layers:
+        q, o = cap[li]
+        for (b, h) in picks:
+            nb = (lens[b] + bs - 1) // bs
+            blocks = bt[sids[b], :nb].long()
+            kk = model.k_cache[blocks, li, h].cpu().unsqueeze(1).unsqueeze(1)       # [nb, 1, 1, bs, D]
+            vv = model.v_cache[blocks, li, h].cpu().unsqueeze(1).unsqueeze(1)
+            qq = q[b, h * g:(h + 1) * g].cpu().unsqueeze(0)                          # [1, g, D]
+            ref = K.paged_attention_exact(qq, kk, vv, torch.arange(nb, dtype=torch.int32).unsqueeze(0), [0], [lens[b]],
+                                          D ** -0.5, bs, 0)                          # fp64 [1, g*D]
+            got = o[b, h * g * D:(h + 1) * g * D].double().cpu()
+            err = float((got - ref[0]).abs().max() / ref.abs().max())
+            worst = max(worst, err)
+            res["attention_rows"].append({"layer": li, "seq": b, "kv_head": h, "rel_err_vs_fp64": err})
+    res["attention_worst_rel_err"] = worst
+    res["attention_tol"] = 8e-3
+    assert worst <= 8e-3, f"paged attention at the benchmarked shape is off the fp64 oracle by {worst:.3e} (> 8e-3 of max|o|)"
+
+    # (b) whole sequences through the CPU oracle with this model's weights and pages
+    if n_seqs > 0:
+        w = OracleWeights(L)
+        mw = model.weight
+        Fd = mc.ffn_inter_dim
+        w.wte, w.lm_head, w.final_norm = mw.wte.cpu(), mw.lm_head.cpu(), mw.final_norm.cpu()
+        nqd, nkvd = nq * D, nkv * D
+        for lw, ml in zip(w.layers, mw.layers):
+            qkv = ml.qkv_proj.cpu()
+            lw.q_proj, lw.k_proj, lw.v_proj = qkv[:nqd], qkv[nqd:nqd + nkvd], qkv[nqd + nkvd:]
+            lw.attn_norm, lw.ffn_norm = ml.attn_norm.cpu(), ml.ffn_norm.cpu()
+            lw.o_proj, lw.up_gate_proj, lw.down_proj = ml.o_proj.cpu(), ml.up_gate_proj.cpu(), ml.down_proj.cpu()
+        seqs = sorted({int(x) for x in torch.randint(0, B, (n_seqs * 4,), generator=rng).tolist()})[:n_seqs]
+        bps = max((lens[b] + bs - 1) // bs for b in seqs)
+        cfgd = dict(hidden_size=mc.hidden_size, num_attention_heads=nq, num_key_value_heads=nkv, intermediate_size=Fd,
+                    num_hidden_layers=L, vocab_size=mc.vocab_size, rms_norm_eps=mc.rms_norm_eps, rope_theta=mc.rope_theta,
+                    max_position_embeddings=mc.max_position_embeddings, rope_scaling=mc.rope_scaling)
+        orc = OracleLlama(cfgd, w, block_size=bs, num_blocks=len(seqs) * bps, num_cpu_blocks=0, max_seqs_in_block_table=len(seqs),
+                          max_blocks_per_seq=bps, attn="exact", dtype=model.dtype)
+        for j, b in enumerate(seqs):
+            nb = (lens[b] + bs - 1) // bs
+            blocks = bt[sids[b], :nb].long()
+            orc.k_cache[j * bps:j * bps + nb] = model.k_cache[blocks].cpu()
+            orc.v_cache[j * bps:j * bps + nb] = model.v_cache[blocks].cpu()
+            orc.gpu_block_manager.allocate_blocks_for_seqs([j], [lens[b]])       # lowest ids first -> j*bps .. j*bps+nb-1
+            assert list(np.asarray(orc.gpu_block_manager.block_table[j][:nb])) == list(range(j * bps, j * bps + nb))
+        ref_toks = orc.forward([ids[b] for b in seqs], list(range(len(seqs))), [lens[b] for b in seqs])
+        ref_logits = orc.last_logits.float()
+        for j, b in enumerate(seqs):
+            rl, gl = ref_logits[j], logits[b]
+            rel = float((gl - rl).abs().max() / rl.abs().max())
+            top2 = torch.topk(rl, 2).values
+            margin = float(top2[0] - top2[1])
+            abs_err = float((gl - rl).abs().max())
+            same = int(toks[b]) == int(ref_toks[j])
+            res["sequences"].append({"seq": b, "token": int(toks[b]), "oracle_token": int(ref_toks[j]), "token_equal": same,
+                                     "logit_rel_err": rel, "oracle_top1_margin": margin, "logit_abs_err": abs_err})
+            assert rel <= 2 ** -5, f"sequence {b}: logits off the CPU oracle by {rel:.3e} of max|logit| (> 2^-5)"
+            assert same or margin <= 2 * abs_err, \
+                f"sequence {b}: token {toks[b]} != oracle {ref_toks[j]} with top-1 margin {margin:.3e} > 2 x logit error {abs_err:.3e}"
+    res["ok"] = True
+    return res
+
+
 # --------------------------------------------------------------------------- GPU arm
 def run_ours(args):
     import torch.distributed as dist
@@ -214,6 +382,10 @@ def run_ours(args):
     if n > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
+
+    ref_triton = None
+    if n == 1 and not args.no_ref_triton and args.model == "llama3-8b" and not args.layers and not args.profile_range:
+        ref_triton = run_reference_triton(args, [d for d in args.ref_triton_dtypes.split(",") if d in ("fp16", "bf16")])
 
     cfg = model_dict(args.model, args.layers)
     mc = swiftllm_b200.LlamaModelConfig(cfg)
@@ -325,10 +497,18 @@ def run_ours(args):
         peak, peak_src = 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
     achieved = alg_bytes / (pa_ms * 1e-3) / 1e9
     traffic, traffic_src = None, None
+    if rank == 0 and not args.no_live_traffic:
+        torch.cuda.synchronize()
+        traffic, traffic_src = measure_traffic_live(args, mc, n)
     tpath = os.path.join(ROOT, "profiles", "paged_attn_traffic.json")
-    if os.path.exists(tpath) and n == 1 and args.model == "llama3-8b" and B == 256 and S == 4096 and not args.layers:
+    if traffic is None and os.path.exists(tpath) and n == 1 and args.model == "llama3-8b" and B == 256 and S == 4096 and not args.layers:
         tj = json.load(open(tpath))
-        traffic, traffic_src = tj["dram_bytes_read"] + tj["dram_bytes_write"], tj["source"]
+        traffic, traffic_src = tj["dram_bytes_read"] + tj["dram_bytes_write"], f"committed constant, {tj['source']} (live ncu: {traffic_src})"
+
+    # ---- parity at the benchmarked shape (outside the timed regions): sampled attention rows + whole sequences vs the oracle
+    parity = None
+    if n == 1 and not args.no_parity:
+        parity = parity_check(model, mc, state["ids"], sids, lens, n_rows=8, n_seqs=args.parity_seqs)
     pa_gen = os.environ.get("SLLM_PAGED_ATTN_GEN", "")
     kname = "paged_attn_kernel (gen 1: cp.async + mma.sync)" if pa_gen == "1" else \
         "paged_attn_tc_kernel (gen 2: tcgen05 + TMA, persistent)"
@@ -384,7 +564,18 @@ def run_ours(args):
         "clocks": clk,
         "cpu_baseline": cpu,
         "prefill": prefill,
+        "parity_at_bench_shape": parity,
     }
+    if ref_triton is not None:
+        e2e_v = line["e2e"]["value"]
+        blk = {"what": "the UNMODIFIED reference (baseline/_ref/src: its Triton kernels + cuBLAS + its own host path) on this GPU, "
+                       "same workload, LlamaModel.forward with host lists in / host ints out (comparable to `e2e`), own process, "
+                       "run before this arm; dummy weights of the reference (values do not affect timing)",
+               "runs": ref_triton}
+        for dt, d in ref_triton.items():
+            if "value" in d:
+                blk[f"e2e_over_reference_{dt}"] = e2e_v / d["value"]
+        line["reference_triton"] = blk
     if args.layers:
         line["reduced"] = "layer count overridden: NOT a valid BASELINE measurement"
     emit(line)

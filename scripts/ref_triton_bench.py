@@ -1,14 +1,36 @@
 """Times the UNMODIFIED reference (swiftLLM, placed under baseline/_ref/src by scripts/install_reference.sh; git-ignored) on the GPU:
-its own Triton kernels + cuBLAS, fp16 as shipped, BASELINE config 2 (Llama-3-8B shapes, pure decode, batch 256,
-seq_len 4096).  Informational companion to bench.py (the contract's `--impl reference` arm is the CPU port):
-prints one JSON line with the reference's decode step time and the time of its paged_attention (phase 1 + 2)."""
-import json, os, statistics, sys, tempfile, types
+its own Triton kernels + cuBLAS, BASELINE config 2 (Llama-3-8B shapes, pure decode, batch 256, seq_len 4096) through its
+own public API (`LlamaModel.forward`: host lists in, host ints out - the same call bench.py's `e2e` leg makes).
+bench.py runs this as a subprocess (N = 1, before it allocates its own model) and reports the result as `reference_triton`;
+the contract's `--impl reference` arm stays the CPU port.  Prints one JSON line: decode step time, tokens/s and the time of
+its paged_attention (phase 1 + 2, CUDA events on the stream the reference launches it on).
+
+REF_DTYPE=fp16 (default): the tree exactly as shipped (it hard-codes fp16, SURVEY.md "Facts").
+REF_DTYPE=bf16: a throw-away COPY of the tree (temp dir, never written back) in which the fp16 literals SURVEY.md lists
+(`torch.float16` / `tl.float16` in swiftllm/**.py) are replaced by their bf16 counterparts - the "dtype-patched reference"
+BASELINE's bf16 metric needs; nothing else is changed."""
+import json, os, re, shutil, statistics, sys, tempfile, types
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 REF = os.path.join(ROOT, "baseline", "_ref", "src")
 if not os.path.isdir(os.path.join(REF, "swiftllm", "worker")):
     print(json.dumps({"impl": "reference-triton", "unavailable": "baseline/_ref/src missing: run scripts/install_reference.sh"})); sys.exit(0)
-sys.path.insert(0, REF)
+DTYPE = os.environ.get("REF_DTYPE", "fp16")
+assert DTYPE in ("fp16", "bf16")
+SRC = REF
+if DTYPE == "bf16":
+    SRC = os.path.join(tempfile.mkdtemp(prefix="ref_bf16_"), "src")
+    shutil.copytree(os.path.join(REF, "swiftllm"), os.path.join(SRC, "swiftllm"))
+    npatched = 0
+    for d, _, fs in os.walk(os.path.join(SRC, "swiftllm")):
+        for f in fs:
+            if f.endswith(".py"):
+                p = os.path.join(d, f); t = open(p).read()
+                t2 = re.sub(r"\b(torch|tl)\.float16\b", r"\1.bfloat16", t)
+                if t2 != t:
+                    npatched += t.count(".float16"); open(p, "w").write(t2)
+    assert npatched >= 10, npatched
+sys.path.insert(0, SRC)
 sys.path.insert(0, os.path.join(REF, "csrc"))          # swiftllm_c built in place (the reference's `pip install -e csrc`)
 import torch
 ray = types.ModuleType("ray"); ray.remote = lambda cls: cls; sys.modules["ray"] = ray
@@ -43,18 +65,20 @@ def timed_paged(*a, **k):
     e0.record(); orig(*a, **k); e1.record(); events.append((e0, e1))
 TL.paged_attention = timed_paged
 ids = [[1]] * B; sids = list(range(B)); lens = [S] * B
-for _ in range(3):
-    model.forward(ids, sids, lens)
+WARMUP = int(os.environ.get("REF_WARMUP", 3))
+for _ in range(WARMUP):
+    ids = [[t] for t in model.forward(ids, sids, lens)]      # sampled tokens fed back, like bench.py's e2e leg
 events.clear()
 torch.cuda.synchronize()
 t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
 t0.record()
 for _ in range(STEPS):
-    model.forward(ids, sids, lens)
+    ids = [[t] for t in model.forward(ids, sids, lens)]
 t1.record(); torch.cuda.synchronize()
 ms = t0.elapsed_time(t1) / STEPS
 pa = statistics.mean(a.elapsed_time(b) for a, b in events)
 alg = B * S * 8 * 128 * 2 * 2 + 2 * B * 32 * 128 * 2
-print(json.dumps({"impl": "reference-triton", "dtype": "fp16 (as shipped)", "metric": "decode_tokens_per_s", "value": B / (ms * 1e-3),
+print(json.dumps({"impl": "reference-triton", "dtype": "fp16 (as shipped)" if DTYPE == "fp16" else "bf16 (fp16 literals patched in a temp copy)",
+                  "kv_cache_dtype": str(model.k_cache.dtype), "seq_block_size_heuristic": "reference (model.py:305-324)", "metric": "decode_tokens_per_s", "value": B / (ms * 1e-3),
                   "ms_per_step": ms, "paged_attention_ms_per_layer": pa, "paged_attention_GBps_algorithmic": alg / (pa * 1e-3) / 1e9,
-                  "batch": B, "seq_len": S, "steps": STEPS, "triton": __import__("triton").__version__, "torch": torch.__version__}))
+                  "batch": B, "seq_len": S, "steps": STEPS, "warmup": WARMUP, "triton": __import__("triton").__version__, "torch": torch.__version__}))

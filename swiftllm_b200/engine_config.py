@@ -27,6 +27,7 @@ class EngineConfig:
     tp_rank: int = 0
     pin_swap_space: bool = True     # the reference's swap space is pageable (model.py:158-159)
     use_cuda_graph: bool = False    # capture pure-decode steps into CUDA graphs
+    max_cuda_graphs: int = 16       # decode graphs kept (keyed by batch size x length bucket), least recently used evicted
     # TP exchange: True = one-shot peer-memory all-reduce fused with add+RMSNorm (tp_comm.py), False = NCCL all-reduce +
     # a separate kernel, None = automatic (fused for tp_size 2..4 where it was measured faster, NCCL otherwise),
     # "two_shot" = the row-owner (reduce-scatter + all-gather) variant of the fused kernel, meant for tp_size 8,

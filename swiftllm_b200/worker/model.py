@@ -100,6 +100,10 @@ class LlamaModel:
         self.cpu_block_manager = self.gpu_block_manager = None
         self.tp_group = None
         self._graphs = {}
+        # pinned staging ring for per-step metadata (eager path): a slot is rewritten only after the H2D copy that last read it
+        # has completed (event per slot), so back-to-back forward_async calls never race the copy engine
+        self._stage_ring = []
+        self._stage_next = 0
 
     # ------------------------------------------------------------------ init
     @torch.inference_mode()
@@ -173,12 +177,27 @@ class LlamaModel:
         block_size_bytes = self.engine_config.block_size * self._kvslot_bytes()
         num_gpu_blocks = math.floor((useable_memory - peak_memory) / block_size_bytes)
         torch.cuda.empty_cache()
+        if self.tp_size > 1:
+            # every rank must run the SAME allocator state (block ids and the out-of-blocks RuntimeError are decided on each
+            # rank's host mirror): take the minimum over ranks
+            t = torch.tensor([num_gpu_blocks], dtype=torch.int64, device=self.device)
+            dist.all_reduce(t, op=dist.ReduceOp.MIN, group=self.tp_group)
+            num_gpu_blocks = int(t.item())
         return num_gpu_blocks
 
     @torch.inference_mode()
     def init_kvcache_and_swap(self, num_blocks: int):
         """model.py:134-175.  KV cache [num_blocks, L, nkv/tp, block_size, D] (zeros, like the reference), CPU swap
         space (pinned here), and the two block managers."""
+        if self.tp_size > 1 and dist.is_initialized():
+            # identical num_blocks on every rank <=> identical block ids and a collective out-of-blocks decision (all ranks
+            # raise the same RuntimeError at the same step instead of one rank leaving its peers inside an exchange)
+            t = torch.tensor([num_blocks, -num_blocks], dtype=torch.int64, device=self.device)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.tp_group)
+            if int(t[0].item()) != num_blocks or int(-t[1].item()) != num_blocks:
+                raise RuntimeError(f"init_kvcache_and_swap: num_blocks differs between tensor-parallel ranks "
+                                   f"(this rank {num_blocks}, min {int(-t[1].item())}, max {int(t[0].item())}); use the value "
+                                   f"profile_num_blocks() returns (it is min-reduced over ranks)")
         self.num_blocks = num_blocks
         mc, ec = self.model_config, self.engine_config
         shape = (num_blocks, mc.num_layers, mc.num_kv_heads // self.tp_size, ec.block_size, mc.head_dim)
@@ -215,10 +234,32 @@ class LlamaModel:
         input_embds += residual_buf
         return self.post_layer.forward(input_embds, infer_state)
 
+    _STAGE_SLOTS = 4
+
+    def _stage_slot(self, n: int):
+        """Next slot of the persistent pinned ring, grown geometrically; waits (host side) for the copy that last used it."""
+        i = self._stage_next
+        self._stage_next = (i + 1) % self._STAGE_SLOTS
+        if len(self._stage_ring) <= i:
+            self._stage_ring.append(None)
+        slot = self._stage_ring[i]
+        if slot is None or slot[0].numel() < n:
+            cap = max(4096, 1 << (max(n, 1) - 1).bit_length())
+            if slot is not None:
+                slot[1].synchronize()
+            slot = (torch.empty((cap,), dtype=torch.int32).pin_memory(), torch.cuda.Event())
+            self._stage_ring[i] = slot
+        else:
+            slot[1].synchronize()                # no-op unless the copy engine is more than _STAGE_SLOTS steps behind
+        return slot
+
     def _stage_metadata(self, *parts):
-        """One pinned host buffer, one async H2D copy; returns int32 device views (one per host list)."""
-        host = torch.tensor(list(itertools.chain(*parts)), dtype=torch.int32).pin_memory()
-        dev = host.to(self.device, non_blocking=True)
+        """One persistent pinned host buffer (ring of slots), one async H2D copy; returns int32 device views (one per list)."""
+        flat = np.fromiter(itertools.chain(*parts), dtype=np.int32)
+        host, ev = self._stage_slot(flat.size)
+        host[:flat.size].numpy()[:] = flat
+        dev = host[:flat.size].to(self.device, non_blocking=True)
+        ev.record()
         views, off = [], 0
         for p in parts:
             views.append(dev[off:off + len(p)])
@@ -317,10 +358,15 @@ class LlamaModel:
         bucket = ((max_len + 1023) // 1024) * 1024
         ws_bytes = _lib.lib().sllm_paged_attention_workspace_bytes(B, nq, mc.head_dim, bucket, 0, nkv)
         key = (B, bucket if ws_bytes > 0 else 0)
-        g = self._graphs.get(key)
+        g = self._graphs.pop(key, None)
         if g is None:
+            # bounded cache (least recently used graph dropped first); all graphs share ONE memory pool - they are replayed
+            # one at a time on one stream and their only output (`tokens`) is copied out before the next replay
+            cap = max(1, int(getattr(self.engine_config, "max_cuda_graphs", 16)))
+            while len(self._graphs) >= cap:
+                self._graphs.pop(next(iter(self._graphs)))
             g = self._capture_decode_graph(B, bucket)
-            self._graphs[key] = g
+        self._graphs[key] = g                    # (re)insert as most recently used
         # host-side bookkeeping of the allocator (exhaustion check + mirror), no device work here
         bm = self.gpu_block_manager
         idx = np.asarray(seq_ids_list, dtype=np.int64)
@@ -333,20 +379,25 @@ class LlamaModel:
                                f"{bm.num_free_blocks} free, {total} requested)")
         bm._host_nsab[idx] = target
         bm.num_free_blocks -= total
-        host = g["host"]
-        host[:B] = torch.tensor(flat_ids, dtype=torch.int32)
-        host[B:2 * B] = torch.tensor(seq_ids_list, dtype=torch.int32)
-        host[2 * B:3 * B] = torch.tensor(lens_list, dtype=torch.int32)
+        # pinned staging: a ring of (buffer, event) pairs per graph; a buffer is rewritten only after the H2D copy that last
+        # read it has finished, so back-to-back forward_async calls are safe
+        i = g["next"]; g["next"] = (i + 1) % len(g["host"])
+        host, ev = g["host"][i]
+        ev.synchronize()
+        hv = host.numpy()
+        hv[:B] = flat_ids; hv[B:2 * B] = seq_ids_list; hv[2 * B:3 * B] = lens_list
         g["meta"].copy_(host, non_blocking=True)
+        ev.record()
         g["graph"].replay()
-        return g["tokens"]
+        # the graph's static output is overwritten by the next replay: hand out a copy (stream-ordered, no sync)
+        return g["tokens"].clone()
 
     def _capture_decode_graph(self, B: int, bucket_len: int):
         from swiftllm_b200.worker.kernels.block_mgmt import allocate_blocks_for_seqs as alloc_kernel
         mc, ec = self.model_config, self.engine_config
         dev = self.device
         meta = torch.zeros((3 * B,), dtype=torch.int32, device=dev)
-        host = torch.zeros((3 * B,), dtype=torch.int32).pin_memory()
+        host = [(torch.zeros((3 * B,), dtype=torch.int32).pin_memory(), torch.cuda.Event()) for _ in range(self._STAGE_SLOTS)]
         ids, seq_ids, lens = meta[:B], meta[B:2 * B], meta[2 * B:]
         last = torch.arange(B, dtype=torch.int32, device=dev)
         empty = torch.empty((0,), dtype=torch.int32, device=dev)
@@ -383,11 +434,13 @@ class LlamaModel:
         torch.cuda.synchronize()
         del k_s, v_s, scratch_bm
         graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(graph):
+        if getattr(self, "_graph_pool", None) is None:
+            self._graph_pool = torch.cuda.graph_pool_handle()
+        with torch.cuda.graph(graph, pool=self._graph_pool):
             tokens = step(self.gpu_block_manager, self.k_cache, self.v_cache)
         torch.cuda.synchronize()
         # `last` / `empty` are read by the captured kernels on every replay: keep them alive with the graph
-        return dict(graph=graph, meta=meta, host=host, tokens=tokens, keep=(last, empty))
+        return dict(graph=graph, meta=meta, host=host, next=0, tokens=tokens, keep=(last, empty))
 
     # ------------------------------------------------------------------ swap / free
     def _swap(self, seq_ids_list: list, is_swap_in: bool):

@@ -45,6 +45,14 @@ class FusedAllReduce:
             self.xout.zero_()
             self._hx = symm_mem.rendezvous(self.xout, group)
         torch.cuda.synchronize(); dist.barrier(group)                  # every rank's flags are zero before first use
+        # the GEMMs write through self.data / self.xout, the kernels read every rank's copy (this rank's included) through the
+        # handle's peer pointers: both must be the same memory
+        for name, t, h in (("data", self.data, self._hd), ("flags", self.flags, self._hf)) + \
+                ((("xout", self.xout, self._hx),) if self.two_shot else ()):
+            if int(h.buffer_ptrs[self.rank]) != t.data_ptr():
+                raise RuntimeError(f"symmetric buffer `{name}`: the rendezvous handle maps this rank's copy at "
+                                   f"{int(h.buffer_ptrs[self.rank]):#x} but the tensor lives at {t.data_ptr():#x} "
+                                   f"(sub-allocated symmetric memory is not supported by the fused exchange)")
         slot_bytes = max_tokens * hidden * self.data.element_size()
         PtrArr = ctypes.c_void_p * self.world
         self._buf_ptrs = [PtrArr(*[int(p) + s * slot_bytes for p in self._hd.buffer_ptrs]) for s in range(NUM_SLOTS)]

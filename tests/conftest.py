@@ -21,6 +21,15 @@ def pytest_collection_modifyitems(config, items):
     """Tests of kernels that have never run on a GPU must not be able to turn the validated suite red (the driver runs
     `-m gpu -x`).  They are opted into with SLLM_RUN_PENDING=1 (scripts/gpu_validate_pending.sh) and lose the marker once
     they have passed on a B200."""
+    import torch
+    lib_built = os.path.exists(os.path.join(ROOT, "swiftllm_b200", "libswiftllm_b200.so"))
+    if not torch.cuda.is_available():
+        # a plain `pytest` on a CPU box: GPU tests are skipped, not failed.  On a GPU box a missing library is NOT skipped -
+        # the tests must fail loudly there (no silent fallback).
+        no_gpu = pytest.mark.skip(reason="needs a CUDA device" + ("" if lib_built else " and libswiftllm_b200.so"))
+        for item in items:
+            if "gpu" in item.keywords:
+                item.add_marker(no_gpu)
     if os.environ.get("SLLM_RUN_PENDING", "") == "1":
         return
     skip = pytest.mark.skip(reason="pending first GPU validation: set SLLM_RUN_PENDING=1 to run")
