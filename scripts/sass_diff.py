@@ -3,6 +3,9 @@
 
     python scripts/sass_diff.py save  <dir>      # dump one normalised .sass per kernel into <dir>
     python scripts/sass_diff.py check <dir>      # report kernels whose instruction stream changed / appeared / vanished
+    python scripts/sass_diff.py manifest <json> "<where validated>"   # hash of every kernel's normalised SASS: written after the
+                                                 # whole `pytest -m gpu` suite, smoke() and bench.py passed on a B200 with this
+                                                 # exact build (tests/test_cabi.py holds later builds to it)
 
 Used when a validated kernel's SOURCE is refactored without a GPU at hand (e.g. moved into a shared template): an
 unchanged instruction stream means the GPU validation of that kernel still stands.  Mangled names are normalised by
@@ -53,6 +56,20 @@ def demangle(names):
 def main():
     mode, d = sys.argv[1], sys.argv[2]
     ks = kernels()
+    if mode == "manifest":
+        import hashlib
+        import json
+        dm = demangle(sorted(ks))
+        nvcc = subprocess.run(["nvcc", "--version"], capture_output=True, text=True).stdout
+        rel = re.search(r"release [0-9.]+, V[0-9.]+", nvcc)
+        man = {"nvcc": rel.group(0) if rel else nvcc.strip().splitlines()[-1], "flags": "see swiftllm_b200/build.py",
+               "validated_at": sys.argv[3] if len(sys.argv) > 3 else "",
+               "kernels": {dm[n]: {"sha256": hashlib.sha256("\n".join(norm(b)).encode()).hexdigest(), "instructions": len(b)}
+                           for n, b in sorted(ks.items())},
+               "equivalent": {}}
+        json.dump(man, open(d, "w"), indent=1)
+        print(f"manifest of {len(ks)} kernels -> {d}")
+        return
     if mode == "save":
         os.makedirs(d, exist_ok=True)
         for n, b in ks.items():

@@ -72,11 +72,18 @@ __global__ void __launch_bounds__(512) allreduce_add_rmsnorm_kernel(const ArPara
     float ss = 0.f;
     for (int i = threadIdx.x; i < nvec; i += blockDim.x) {
         float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-#pragma unroll 1
-        for (int r = 0; r < p.nranks; r++) {                 // fixed order on every rank -> identical sums
-            Vec8<T> v = ld_vec8_peer(reinterpret_cast<const T*>(p.peer_buf[r]) + t * p.hidden + 8 * i);
+        // all N peer loads are issued before the first one is consumed (one NVLink round trip instead of N in series);
+        // the accumulation below keeps the fixed rank order -> identical sums on every rank
+        Vec8<T> pv[AR_MAX_RANKS];
 #pragma unroll
-            for (int j = 0; j < 4; j++) { float2 f = TT::to_f2(v.v[j]); acc[2 * j] += f.x; acc[2 * j + 1] += f.y; }
+        for (int r = 0; r < AR_MAX_RANKS; r++)
+            if (r < p.nranks) pv[r] = ld_vec8_peer(reinterpret_cast<const T*>(p.peer_buf[r]) + t * p.hidden + 8 * i);
+#pragma unroll
+        for (int r = 0; r < AR_MAX_RANKS; r++) {
+            if (r < p.nranks) {
+#pragma unroll
+                for (int j = 0; j < 4; j++) { float2 f = TT::to_f2(pv[r].v[j]); acc[2 * j] += f.x; acc[2 * j + 1] += f.y; }
+            }
         }
         Vec8<T> a, b = ld_vec8(rr + 8 * i);
 #pragma unroll
@@ -204,11 +211,16 @@ __global__ void __launch_bounds__(512) allreduce_add_rmsnorm_2shot_kernel(const 
                 sum = multimem_ld_reduce_add<T>(reinterpret_cast<const T*>(p.mc_buf) + t * p.hidden + 8 * i);
             } else {
                 float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-#pragma unroll 1
-                for (int r = 0; r < p.nranks; r++) {
-                    Vec8<T> v = ld_vec8_peer(reinterpret_cast<const T*>(p.peer_buf[r]) + t * p.hidden + 8 * i);
+                Vec8<T> pv[AR_MAX_RANKS];                           // N independent peer loads in flight, summed in rank order
 #pragma unroll
-                    for (int j = 0; j < 4; j++) { float2 f = TT::to_f2(v.v[j]); acc[2 * j] += f.x; acc[2 * j + 1] += f.y; }
+                for (int r = 0; r < AR_MAX_RANKS; r++)
+                    if (r < p.nranks) pv[r] = ld_vec8_peer(reinterpret_cast<const T*>(p.peer_buf[r]) + t * p.hidden + 8 * i);
+#pragma unroll
+                for (int r = 0; r < AR_MAX_RANKS; r++) {
+                    if (r < p.nranks) {
+#pragma unroll
+                        for (int j = 0; j < 4; j++) { float2 f = TT::to_f2(pv[r].v[j]); acc[2 * j] += f.x; acc[2 * j + 1] += f.y; }
+                    }
                 }
 #pragma unroll
                 for (int j = 0; j < 4; j++) sum.v[j] = TT::from_f2(make_float2(acc[2 * j], acc[2 * j + 1]));
@@ -243,11 +255,13 @@ __global__ void __launch_bounds__(512) allreduce_add_rmsnorm_2shot_kernel(const 
             if constexpr (NVLS) {
                 multimem_st<T>(reinterpret_cast<T*>(p.mc_xout) + t * p.hidden + 8 * i, o);
             } else {
-#pragma unroll 1
-                for (int k = 0; k < p.nranks; k++) {
-                    int r = p.rank + 1 + k;
-                    if (r >= p.nranks) r -= p.nranks;
-                    st_vec8_peer(reinterpret_cast<T*>(p.peer_xout[r]) + t * p.hidden + 8 * i, o);
+#pragma unroll
+                for (int k = 0; k < AR_MAX_RANKS; k++) {
+                    if (k < p.nranks) {
+                        int r = p.rank + 1 + k;
+                        if (r >= p.nranks) r -= p.nranks;
+                        st_vec8_peer(reinterpret_cast<T*>(p.peer_xout[r]) + t * p.hidden + 8 * i, o);
+                    }
                 }
             }
         }

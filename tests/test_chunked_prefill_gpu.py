@@ -3,8 +3,7 @@
   sllm_prefill_attention_paged    both kernel generations vs the fp64 definition; with prefix 0 vs sllm_prefill_attention
   LlamaModel.forward(..., prefill_prefix_lens_list=...)   chunked == whole-prompt (tokens exact, logits within tolerance)
 
-PENDING: written and cross-compiled for sm_100a in a session that had no GPU time left; never executed on hardware.
-Run with SLLM_RUN_PENDING=1 (scripts/gpu_validate_pending.sh); drop the `pending_gpu` marker once green on a B200."""
+First executed on a B200 in round 2 (green on the first run: profiles/r2_pytest_pending_1gpu.log); part of the default `-m gpu` suite."""
 import types
 
 import numpy as np
@@ -14,7 +13,7 @@ import torch
 from oracle import kernels as K
 from oracle.model import OracleLlama, OracleWeights
 
-pytestmark = [pytest.mark.gpu, pytest.mark.pending_gpu]
+pytestmark = pytest.mark.gpu
 DEV = "cuda"
 DTYPES = [torch.float16, torch.bfloat16]
 

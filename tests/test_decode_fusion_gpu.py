@@ -1,8 +1,7 @@
 """GPU: decode-step fusion - rotary embedding + KV store of the new rows in one launch (sllm_rotary_store_kvcache_decode,
 csrc/rotary_store.cu; EngineConfig.fuse_rotary_store) against the two separate kernels (bit for bit) and the oracle.
 
-PENDING: written and cross-compiled for sm_100a in a session that had no GPU time left; never executed on hardware.
-Run with SLLM_RUN_PENDING=1 (scripts/gpu_validate_pending.sh); drop the `pending_gpu` marker once green on a B200."""
+First executed on a B200 in round 2 (green on the first run: profiles/r2_pytest_pending_1gpu.log); part of the default `-m gpu` suite."""
 import numpy as np
 import pytest
 import torch
@@ -11,7 +10,7 @@ from oracle import kernels as K
 from oracle.model import OracleWeights
 from test_chunked_prefill_gpu import CFG, DEV, DTYPES, NS, _layout, i32
 
-pytestmark = [pytest.mark.gpu, pytest.mark.pending_gpu]
+pytestmark = pytest.mark.gpu
 
 
 # ----------------------------------------------------------------------------- fused rotary + KV store (decode rows)

@@ -1,4 +1,4 @@
-"""CPU dry run of the GPU tests that are still `pending_gpu` (tests/test_chunked_prefill_gpu.py, test_decode_fusion_gpu.py,
+"""CPU dry run of GPU tests whose kernels were written without GPU access (tests/test_chunked_prefill_gpu.py, test_decode_fusion_gpu.py,
 test_swap_device_gpu.py): the test FUNCTIONS are executed here with every kernel wrapper replaced by the oracle's restatement
 (tests/cpu_shim.py) and "cuda" mapped to the CPU.  This cannot say anything about the kernels; it makes sure the tests
 themselves - shapes, metadata, oracle calls, assertions, the model-level schedules - are sound, so that the first GPU minutes

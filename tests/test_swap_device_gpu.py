@@ -1,8 +1,7 @@
 """GPU: swap with device-resident id lists (sllm_swap_blocks_gathered, csrc/swap_gather.cu; EngineConfig.device_swap) against the
 oracle and the memcpy path (swiftllm_c.swap_blocks): exact bytes, K and V, scattered and consecutive ids, both directions.
 
-PENDING: written and cross-compiled for sm_100a in a session that had no GPU time left; never executed on hardware.
-Run with SLLM_RUN_PENDING=1 (scripts/gpu_validate_pending.sh); drop the `pending_gpu` marker once green on a B200."""
+First executed on a B200 in round 2 (green on the first run: profiles/r2_pytest_pending_1gpu.log); part of the default `-m gpu` suite."""
 import numpy as np
 import pytest
 import torch
@@ -10,7 +9,7 @@ import torch
 from oracle import kernels as K
 from oracle.model import OracleWeights
 
-pytestmark = [pytest.mark.gpu, pytest.mark.pending_gpu]
+pytestmark = pytest.mark.gpu
 DEV = "cuda"
 
 

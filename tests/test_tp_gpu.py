@@ -13,7 +13,21 @@ CFG = dict(model_type="llama", num_hidden_layers=3, num_attention_heads=8, num_k
            hidden_act="silu")
 
 
-def _run(rank, world, port, q):
+# 8 kv heads (head_dim stays 128): shards down to 1 kv head / 2 q heads per rank at world 8
+CFG8 = dict(CFG, hidden_size=2048, num_attention_heads=16, num_key_value_heads=8)
+
+# (name, fused_allreduce, shard_lm_head, fuse_rotary_store): every exchange / sharding variant of the TP data plane
+MODES = [("nccl", False, False, False),
+         ("fused-one-shot", True, False, False),
+         ("fused-two-shot", "two_shot", False, False),
+         ("fused-two-shot-nvls", "two_shot_nvls", False, False),
+         ("nccl+sharded-lm-head+rotary-store", False, True, True),
+         ("two-shot+sharded-lm-head+rotary-store", "two_shot", True, True)]
+
+
+def _run(rank, world, port, q, mode_names):
+    """One process per GPU; ALL requested modes run in this one process group (one NCCL init per world size instead of one
+    per mode: multi-GPU box time is charged per GPU)."""
     import numpy as np
     import torch.distributed as dist
     import swiftllm_b200
@@ -21,129 +35,106 @@ def _run(rank, world, port, q):
     os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
     torch.cuda.set_device(rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    cfg = CFG8 if world > 4 else CFG
 
-    def make(tp, r, graph=False, fused=False):
+    def make(tp, r, graph=False, fused=False, shard=False, frs=False):
         ec = swiftllm_b200.EngineConfig(model_path="", use_dummy=False, block_size=16, gpu_mem_utilization=0.9, num_cpu_blocks=2,
                                         max_seqs_in_block_table=8, max_blocks_per_seq=16, max_batch_size=4, max_tokens_in_batch=256,
                                         dtype="bfloat16", tp_size=tp, tp_rank=r, use_cuda_graph=graph, fused_allreduce=fused,
-                                        shard_lm_head=os.environ.get("SLLM_TEST_SHARD_LM_HEAD", "0") == "1")
-        m = swiftllm_b200.LlamaModel(ec, swiftllm_b200.LlamaModelConfig(CFG))
+                                        shard_lm_head=shard, fuse_rotary_store=frs)
+        m = swiftllm_b200.LlamaModel(ec, swiftllm_b200.LlamaModelConfig(cfg))
         m.load_weights(synthetic_getter(seed=11, std=0.05, device=f"cuda:{rank}"))
         m.init_kvcache_and_swap(40)
         m.post_layer.keep_logits = True
         return m
-    fused = {"0": False, "1": True, "2": "two_shot", "3": "two_shot_nvls"}[os.environ.get("SLLM_TEST_FUSED_AR", "0")]
-    tp = make(world, rank, fused=fused)
-    tpg = make(world, rank, graph=True, fused=fused)
-    ref = make(1, 0) if rank == 0 else None
-    rng = np.random.default_rng(3)
-    prompts = [rng.integers(0, 1000, size=n).tolist() for n in (40, 7, 129)]
-    sids = [5, 0, 2]
-    worst = 0.0
-    toks = tp.forward(prompts, sids, []); tg = tpg.forward(prompts, sids, [])
-    assert toks == tg
-    lens = [len(p) for p in prompts]
-    rt = ref.forward(prompts, sids, []) if ref else None
-    for step in range(6):
-        if ref:
-            a, b = tp.post_layer.last_logits.float(), ref.post_layer.last_logits.float()
-            rel = float((a - b).abs().max() / b.abs().max()); worst = max(worst, rel)
-            top2 = b.topk(2, dim=1).values
-            clear = ((top2[:, 0] - top2[:, 1]) > 2 * 2 ** -5 * b.abs().max()).tolist()
-            assert rel <= 2 ** -5, rel
-            for x, y, c in zip(toks, rt, clear):
-                if c:
-                    assert x == y
-            n = ref.gpu_block_manager.num_seq_allocated_blocks
-            assert torch.equal(tp.gpu_block_manager.num_seq_allocated_blocks, n)
-            for s in sids:
-                k = int(n[s])
-                assert torch.equal(tp.gpu_block_manager.block_table[s, :k], ref.gpu_block_manager.block_table[s, :k])
-        # all ranks must feed the same tokens: use rank 0's reference tokens
-        feed = [rt if ref else None]
-        dist.broadcast_object_list(feed, src=0)
-        lens = [l + 1 for l in lens]
-        ids = [[t] for t in feed[0]]
-        toks = tp.forward(ids, sids, lens); tg = tpg.forward(ids, sids, lens)
-        assert toks == tg                                  # CUDA-graph decode with NCCL inside == eager
-        if ref:
-            rt = ref.forward(ids, sids, lens)
+
+    results = {}
+    for name, fused, shard, frs in [m for m in MODES if m[0] in mode_names]:
+        tp = make(world, rank, fused=fused, shard=shard, frs=frs)
+        tpg = make(world, rank, graph=True, fused=fused, shard=shard, frs=frs)
+        ref = make(1, 0) if rank == 0 else None
+        rng = np.random.default_rng(3)
+        prompts = [rng.integers(0, 1000, size=n).tolist() for n in (40, 7, 129)]
+        sids = [5, 0, 2]
+        worst = 0.0
+        toks = tp.forward(prompts, sids, []); tg = tpg.forward(prompts, sids, [])
+        assert toks == tg, name
+        lens = [len(p) for p in prompts]
+        rt = ref.forward(prompts, sids, []) if ref else None
+        for step in range(6):
+            if ref:
+                a, b = tp.post_layer.last_logits.float(), ref.post_layer.last_logits.float()
+                rel = float((a - b).abs().max() / b.abs().max()); worst = max(worst, rel)
+                top2 = b.topk(2, dim=1).values
+                clear = ((top2[:, 0] - top2[:, 1]) > 2 * 2 ** -5 * b.abs().max()).tolist()
+                assert rel <= 2 ** -5, (name, rel)
+                for x, y, c in zip(toks, rt, clear):
+                    if c:
+                        assert x == y, name
+                n = ref.gpu_block_manager.num_seq_allocated_blocks
+                assert torch.equal(tp.gpu_block_manager.num_seq_allocated_blocks, n), name
+                for s in sids:
+                    k = int(n[s])
+                    assert torch.equal(tp.gpu_block_manager.block_table[s, :k], ref.gpu_block_manager.block_table[s, :k]), name
+            # all ranks must feed the same tokens: use rank 0's reference tokens
+            feed = [rt if ref else None]
+            dist.broadcast_object_list(feed, src=0)
+            lens = [l + 1 for l in lens]
+            ids = [[t] for t in feed[0]]
+            toks = tp.forward(ids, sids, lens); tg = tpg.forward(ids, sids, lens)
+            assert toks == tg, name                            # CUDA-graph decode with the exchange inside == eager
+            if ref:
+                rt = ref.forward(ids, sids, lens)
+        results[name] = worst
+        # NCCL kernels captured in live CUDA graphs make later collectives / teardown block: drop the graphs first
+        tpg._graphs.clear(); torch.cuda.synchronize(); dist.barrier(); torch.cuda.synchronize()
+        del tp, tpg, ref
     if rank == 0:
-        q.put(worst)
-    # NCCL kernels captured in live CUDA graphs make destroy_process_group() block: drop the graphs and hard-exit
-    tpg._graphs.clear(); torch.cuda.synchronize(); dist.barrier(); torch.cuda.synchronize()
+        q.put(results)
     import time
     time.sleep(0.5)            # let the parent drain the queue
     os._exit(0)
 
 
-@pytest.mark.parametrize("fused", [False, True], ids=["nccl", "fused-p2p"])
-@pytest.mark.parametrize("world", [2, 4])
-def test_tp_matches_single_gpu(world, fused, monkeypatch):
-    if torch.cuda.device_count() < world:
-        pytest.skip(f"needs {world} GPUs")
-    monkeypatch.setenv("SLLM_TEST_FUSED_AR", "1" if fused else "0")
+def _spawn(world, mode_names, port):
     import torch.multiprocessing as mp
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    procs = [ctx.Process(target=_run, args=(r, world, 29650 + world + (10 if fused else 0), q)) for r in range(world)]
+    procs = [ctx.Process(target=_run, args=(r, world, port, q, mode_names)) for r in range(world)]
     for p in procs:
         p.start()
-    worst = q.get(timeout=300)
+    try:
+        results = q.get(timeout=420)
+    finally:
+        for p in procs:
+            p.join(timeout=60)
+            if p.exitcode is None:
+                p.kill()
     for p in procs:
-        p.join(timeout=60)
-        if p.exitcode is None:
-            p.kill()
         assert p.exitcode == 0
-    assert worst <= 2 ** -5
+    return results
 
 
-@pytest.mark.pending_gpu
-@pytest.mark.parametrize("world", [2, 4])
-def test_tp_vocab_sharded_lm_head_matches_single_gpu(world, monkeypatch):
-    """shard_lm_head=True (V / world logit columns per rank + one all-gather of (max, argmax) pairs, also inside the CUDA graph)
-    against the TP=1 model: same checks as above.  PENDING first GPU run (CPU/gloo version: tests/test_tp_gloo.py)."""
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_tp_matches_single_gpu(world):
+    """NCCL all-reduce + add/norm kernel, and the one-shot fused peer-memory exchange, against TP = 1 (eager and CUDA graph)."""
     if torch.cuda.device_count() < world:
         pytest.skip(f"needs {world} GPUs")
-    monkeypatch.setenv("SLLM_TEST_FUSED_AR", "0")
-    monkeypatch.setenv("SLLM_TEST_SHARD_LM_HEAD", "1")
-    import torch.multiprocessing as mp
-    ctx = mp.get_context("spawn")
-    q = ctx.Queue()
-    procs = [ctx.Process(target=_run, args=(r, world, 29690 + world, q)) for r in range(world)]
-    for p in procs:
-        p.start()
-    worst = q.get(timeout=300)
-    for p in procs:
-        p.join(timeout=60)
-        if p.exitcode is None:
-            p.kill()
-        assert p.exitcode == 0
-    assert worst <= 2 ** -5
+    res = _spawn(world, ["nccl", "fused-one-shot"], 29650 + world)
+    print("TP parity (worst logit rel. err. vs TP=1):", world, res)
+    assert set(res) == {"nccl", "fused-one-shot"} and max(res.values()) <= 2 ** -5
 
 
-@pytest.mark.pending_gpu
-@pytest.mark.parametrize("mode", ["2", "3"], ids=["p2p", "nvls-multimem"])
-@pytest.mark.parametrize("world", [2, 4])
-def test_tp_two_shot_fused_exchange_matches_single_gpu(world, mode, monkeypatch):
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_tp_two_shot_exchange_and_sharded_lm_head_match_single_gpu(world):
     """fused_allreduce="two_shot" (row owner reduces + adds + normalises, pushes the row to every rank; residual sharded by
-    rows) against the TP=1 model, eager and inside CUDA graphs; prompts of 40 / 7 / 129 tokens exercise rows without an owner
-    CTA on some ranks and T not divisible by the world size.  nvls-multimem: the reduction and the broadcast done by the NVSwitch
-    (multimem.ld_reduce / multimem.st on the symmetric buffers' multicast addresses).  PENDING first GPU run."""
+    rows) with peer loads / stores and with the NVSwitch doing the reduction and the broadcast (multimem.ld_reduce /
+    multimem.st); vocabulary-sharded lm_head (+ fused rotary / KV store) with both exchanges - against TP = 1, eager and inside
+    CUDA graphs.  Prompts of 40 / 7 / 129 tokens exercise rows without an owner CTA on some ranks and T not divisible by the
+    world size."""
     if torch.cuda.device_count() < world:
         pytest.skip(f"needs {world} GPUs")
-    monkeypatch.setenv("SLLM_TEST_FUSED_AR", mode)
-    monkeypatch.setenv("SLLM_TEST_SHARD_LM_HEAD", "0")
-    import torch.multiprocessing as mp
-    ctx = mp.get_context("spawn")
-    q = ctx.Queue()
-    procs = [ctx.Process(target=_run, args=(r, world, 29720 + world + 10 * int(mode), q)) for r in range(world)]
-    for p in procs:
-        p.start()
-    worst = q.get(timeout=300)
-    for p in procs:
-        p.join(timeout=60)
-        if p.exitcode is None:
-            p.kill()
-        assert p.exitcode == 0
-    assert worst <= 2 ** -5
+    names = ["fused-two-shot", "fused-two-shot-nvls", "nccl+sharded-lm-head+rotary-store", "two-shot+sharded-lm-head+rotary-store"]
+    res = _spawn(world, names, 29690 + world)
+    print("TP parity (worst logit rel. err. vs TP=1):", world, res)
+    assert set(res) == set(names) and max(res.values()) <= 2 ** -5
