@@ -37,6 +37,14 @@ METRIC = "decode_tokens_per_s"
 UNIT = "tokens/s"
 
 
+_T0 = time.perf_counter()
+
+
+def stage(msg: str):
+    """Progress line on stderr: where the wall time of a run goes (the JSON line on stdout is the only stdout output)."""
+    sys.stderr.write(f"[bench +{time.perf_counter() - _T0:6.1f}s] {msg}\n"); sys.stderr.flush()
+
+
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -54,6 +62,10 @@ def parse():
                     help="TP: the row-owner (reduce-scatter + all-gather) variant of the fused exchange (meant for tp 8)")
     ap.add_argument("--nvls-allreduce", dest="fused_allreduce", action="store_const", const="two_shot_nvls",
                     help="TP: two-shot fused exchange with in-switch reduction / broadcast (multimem.ld_reduce / multimem.st)")
+    ap.add_argument("--ll-allreduce", dest="fused_allreduce", action="store_const", const="ll",
+                    help="TP: barrier-free push exchange (LL protocol) for decode-sized steps, two-shot above 1024 rows")
+    ap.add_argument("--ll-nvls-allreduce", dest="fused_allreduce", action="store_const", const="ll_nvls",
+                    help="TP: the LL exchange with the normalised rows broadcast by the NVSwitch (multimem.st)")
     ap.add_argument("--nccl-allreduce", dest="fused_allreduce", action="store_false",
                     help="TP: force NCCL all-reduce + separate add/norm kernel")
     ap.add_argument("--shard-lm-head", action="store_true",
@@ -65,6 +77,7 @@ def parse():
                     help="skip timing the unmodified reference's Triton path (baseline/_ref/src) on this GPU (N = 1 only)")
     ap.add_argument("--ref-triton-dtypes", type=str, default="fp16,bf16",
                     help="reference Triton arm: fp16 = the tree as shipped, bf16 = its fp16 literals patched in a temp copy")
+    ap.add_argument("--ref-triton-timeout", type=int, default=240, help="seconds per dtype for the reference Triton arm")
     ap.add_argument("--no-parity", action="store_true", help="skip the oracle parity check at the benchmarked shape")
     ap.add_argument("--parity-seqs", type=int, default=2, help="sequences re-run through the CPU oracle (tokens + logits)")
     ap.add_argument("--no-live-traffic", action="store_true", help="skip the ncu DRAM-byte measurement of the decode kernel")
@@ -213,19 +226,34 @@ def run_reference_triton(args, dtypes):
     warm-up, CUDA events around the K steps.  Returns {dtype: json-line-or-error}."""
     out = {}
     script = os.path.join(ROOT, "scripts", "ref_triton_bench.py")
+    last = {}
+    try:
+        last = json.load(open(os.path.join(ROOT, "profiles", "ref_triton_last_measured.json")))
+    except Exception:  # noqa: BLE001
+        pass
     for dt in dtypes:
+        stage(f"reference Triton arm ({dt}) ...")
         env = dict(os.environ, REF_DTYPE=dt, REF_BATCH=str(args.batch), REF_SEQLEN=str(args.seqlen),
                    REF_STEPS=str(args.steps), REF_WARMUP=str(max(args.warmup, 3)), CUDA_VISIBLE_DEVICES=os.environ.get("CUDA_VISIBLE_DEVICES", "0"))
         t0 = time.perf_counter()
         try:
-            r = subprocess.run([sys.executable, script], env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=900)
+            r = subprocess.run([sys.executable, script], env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True,
+                               timeout=args.ref_triton_timeout)
             lines = [l for l in r.stdout.strip().splitlines() if l.startswith("{")]
             if r.returncode == 0 and lines:
                 d = json.loads(lines[-1])
             else:
                 d = {"error": f"rc={r.returncode}: " + (r.stderr.strip().splitlines()[-1][:300] if r.stderr.strip() else "no output")}
+        except subprocess.TimeoutExpired:
+            # Cold Triton cache: the reference's phase-1 kernel unrolls 128 pages (tl.static_range, paged_attn.py:88) and is
+            # compiled three times (cur_layer specialisations); ptxas needs ~8 minutes for that.  scripts/ref_triton_bench.py
+            # reads a pre-built cache from baseline/_ref/triton_cache when it travelled with the repo.
+            d = {"error": f"timed out after {args.ref_triton_timeout} s (cold Triton JIT cache: ~8 min of ptxas for the reference's "
+                          f"128-way unrolled kernel)"}
         except Exception as e:  # noqa: BLE001
             d = {"error": str(e)[:300]}
+        if "error" in d and dt in last:
+            d["last_measured"] = last[dt]            # committed record of an earlier run on a B200 (profiles/), labelled as such
         d["wall_s"] = round(time.perf_counter() - t0, 1)
         out[dt] = d
     return out
@@ -245,7 +273,7 @@ def measure_traffic_live(args, mc, n):
            "--seqlen", str(args.seqlen), "--nq", str(mc.num_q_heads // n), "--nkv", str(mc.num_kv_heads // n),
            "--head-dim", str(mc.head_dim)]
     try:
-        r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=300,
+        r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=150,
                            env=dict(os.environ, SLLM_PAGED_ATTN_GEN=os.environ.get("SLLM_PAGED_ATTN_GEN", "")))
     except Exception as e:  # noqa: BLE001
         return None, f"ncu failed: {str(e)[:120]}"
@@ -387,6 +415,7 @@ def run_ours(args):
     if n == 1 and not args.no_ref_triton and args.model == "llama3-8b" and not args.layers and not args.profile_range:
         ref_triton = run_reference_triton(args, [d for d in args.ref_triton_dtypes.split(",") if d in ("fp16", "bf16")])
 
+    stage("building the model shard + KV cache")
     cfg = model_dict(args.model, args.layers)
     mc = swiftllm_b200.LlamaModelConfig(cfg)
     B, S, bs = args.batch, args.seqlen, 16
@@ -450,6 +479,7 @@ def run_ours(args):
         torch.cuda.synchronize()
         torch.cuda.profiler.stop()
         return
+    stage("timed region: e2e, then device-resident")
     clocks = ClockSampler(local_rank)
     if rank == 0:
         clocks.start()
@@ -474,6 +504,7 @@ def run_ours(args):
     ms_val = timed(step_resident, args.steps)
     clk = clocks.stop() if rank == 0 else None
 
+    stage("roofline pass (events around every decode-attention launch)")
     # ---- roofline of the dominant kernel (paged decode attention): eager steps with events around each launch
     model.engine_config.use_cuda_graph = False
     pa_mod.TIMING_EVENTS = []
@@ -498,6 +529,7 @@ def run_ours(args):
     achieved = alg_bytes / (pa_ms * 1e-3) / 1e9
     traffic, traffic_src = None, None
     if rank == 0 and not args.no_live_traffic:
+        stage("live DRAM traffic of the decode kernel (ncu subprocess)")
         torch.cuda.synchronize()
         traffic, traffic_src = measure_traffic_live(args, mc, n)
     tpath = os.path.join(ROOT, "profiles", "paged_attn_traffic.json")
@@ -508,6 +540,7 @@ def run_ours(args):
     # ---- parity at the benchmarked shape (outside the timed regions): sampled attention rows + whole sequences vs the oracle
     parity = None
     if n == 1 and not args.no_parity:
+        stage("oracle parity at the benchmarked shape")
         parity = parity_check(model, mc, state["ids"], sids, lens, n_rows=8, n_seqs=args.parity_seqs)
     pa_gen = os.environ.get("SLLM_PAGED_ATTN_GEN", "")
     kname = "paged_attn_kernel (gen 1: cp.async + mma.sync)" if pa_gen == "1" else \
@@ -516,6 +549,7 @@ def run_ours(args):
     # ---- optional: prefill tokens/s (secondary metric of BASELINE.json)
     prefill = None
     if not args.no_prefill:
+        stage("prefill tokens/s")
         try:
             model.free_seqs_resources(sids)
             Bp, Lp = 4, 4096
@@ -538,6 +572,7 @@ def run_ours(args):
 
     cpu = None
     if n == 1 and not args.no_cpu_baseline:
+        stage("CPU baseline (oracle port, bounded sample)")
         tok_s, sample, _ = cpu_decode_sample(cfg, B, S, args.cpu_sample_seqs)
         cpu = {"value": tok_s, "unit": UNIT, "cores": cpu_threads(), "kind": "port", "sample": sample}
 
@@ -556,7 +591,9 @@ def run_ours(args):
                      "algorithmic_bytes_per_launch": alg_bytes, "mean_launch_ms": pa_ms, "launches_timed": len(durs),
                      "how": "CUDA events around every paged_attention launch over K eager decode steps on the launching stream"},
         "tp_exchange": None if n == 1 else (
-            ("fused NVLS reduce-scatter + add + rmsnorm + all-gather (one kernel, two-shot, multimem)" if getattr(model.comm, "nvls", False)
+            ("fused barrier-free push exchange (LL tags in the data): reduce-scatter + add + rmsnorm + all-gather in one kernel"
+             + (", all-gather by multimem.st" if model.comm.nvls else "") if getattr(model.comm, "ll", False)
+             else "fused NVLS reduce-scatter + add + rmsnorm + all-gather (one kernel, two-shot, multimem)" if getattr(model.comm, "nvls", False)
              else "fused peer-memory reduce-scatter + add + rmsnorm + all-gather (one kernel, two-shot)" if model.comm.two_shot
              else "fused peer-memory all-reduce + add + rmsnorm (one kernel)") if model.comm is not None
             else "ncclAllReduce + fused_add_rmsnorm"),
@@ -578,6 +615,7 @@ def run_ours(args):
         line["reference_triton"] = blk
     if args.layers:
         line["reduced"] = "layer count overridden: NOT a valid BASELINE measurement"
+    stage("done")
     emit(line)
     _finish_distributed(model, n)
 

@@ -186,6 +186,19 @@ int sllm_allreduce_add_rmsnorm_2shot(const void* const* host_peer_bufs, void* co
                                      int slot, void* epoch_state, void* residual, const void* weight, float eps,
                                      int64_t num_tokens, int hidden, sllm_dtype_t dtype, sllm_stream_t stream);
 
+/* Low-latency variant for decode-sized exchanges (csrc/allreduce_ll.cu): same result as the two-shot call (row t reduced, added
+ * to the residual and normalised by rank t % nranks, residual maintained for owned rows only), but WITHOUT barriers: partial rows
+ * are pushed to their owner and normalised rows to every rank as 16-byte lines {payload, epoch tag, payload, epoch tag} that the
+ * receiver polls ("LL" protocol); the complete plain rows appear in x_out (local).  partial: this rank's [num_tokens, hidden]
+ * GEMM output (local).  host_peer_rs_recv / host_peer_ag_recv: HOST arrays of `nranks` DEVICE pointers to every rank's receive
+ * buffers OF THIS SLOT (symmetric memory, zeroed once): rs_recv [nranks][rows_per_rank][hidden], ag_recv [>= num_tokens][hidden],
+ * 4 bytes per element.  mc_ag_recv: NVLS multicast address of ag_recv (one multimem.st per line instead of nranks-1 peer stores)
+ * or NULL.  num_tokens <= nranks * rows_per_rank.  epoch_state as above (shared with the other exchange calls of the slot). */
+int sllm_allreduce_add_rmsnorm_ll(const void* partial, void* const* host_peer_rs_recv, void* const* host_peer_ag_recv,
+                                  void* mc_ag_recv, int rank, int nranks, int slot, void* epoch_state, void* x_out,
+                                  void* residual, const void* weight, float eps, int64_t num_tokens, int hidden,
+                                  int64_t rows_per_rank, sllm_dtype_t dtype, sllm_stream_t stream);
+
 /* ---- Block swapping: csrc/src/block_swapping.cpp:22-85 (swiftllm_c.swap_blocks, csrc/src/entrypoints.cpp:5-7)
  * host_src_ids/host_dst_ids: HOST arrays of n block ids.  k_swap/v_swap: HOST memory (pinned or pageable),
  * k_cache/v_cache: device.  block_bytes = bytes of one block (all layers/heads) of k_cache.

@@ -27,10 +27,14 @@ VARIANTS = {
     "one_shot": (True, False, False),
     "two_shot": ("two_shot", False, False),
     "nvls": ("two_shot_nvls", False, False),
+    "ll": ("ll", False, False),
+    "ll_nvls": ("ll_nvls", False, False),
     "nccl+lmhead+rs": (False, True, True),
     "one_shot+lmhead+rs": (True, True, True),
     "two_shot+lmhead+rs": ("two_shot", True, True),
     "nvls+lmhead+rs": ("two_shot_nvls", True, True),
+    "ll+lmhead+rs": ("ll", True, True),
+    "ll_nvls+lmhead+rs": ("ll_nvls", True, True),
 }
 
 
@@ -115,7 +119,8 @@ def main():
                 ms = timed(step_resident, args.steps)
                 line.update({"ms_per_step": ms, "tokens_per_s": B / (ms * 1e-3), "e2e_ms_per_step": ms_e2e,
                              "e2e_tokens_per_s": B / (ms_e2e * 1e-3),
-                             "exchange": "nccl" if model.comm is None else ("nvls" if model.comm.nvls else "two_shot" if model.comm.two_shot else "one_shot"),
+                             "exchange": "nccl" if model.comm is None else (("ll_nvls" if model.comm.nvls else "ll") if model.comm.ll else "nvls" if model.comm.nvls
+                                                                            else "two_shot" if model.comm.two_shot else "one_shot"),
                              "lm_head_sharded": bool(shard), "fuse_rotary_store": bool(frs)})
                 if name in args.profile.split(","):
                     # every rank must replay (the exchange is collective); only rank 0 records

@@ -39,6 +39,7 @@ SIGNATURES = {
     "sllm_allocate_blocks_for_seqs": (_I, [_P, _P, _P, _P, _P, _I, _I, _L, _I, _P, _L, _P, _P]),
     "sllm_allreduce_add_rmsnorm": (_I, [_P, _P, _I, _I, _I, _P, _P, _P, _P, _F, _L, _I, _I, _P]),
     "sllm_allreduce_add_rmsnorm_2shot": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _P, _P, _P, _F, _L, _I, _I, _P]),
+    "sllm_allreduce_add_rmsnorm_ll": (_I, [_P, _P, _P, _P, _I, _I, _I, _P, _P, _P, _P, _F, _L, _I, _L, _I, _P]),
     "sllm_swap_blocks": (_I, [_P, _P, _L, _I, _P, _P, _P, _P, _L, _P]),
     "sllm_swap_blocks_gathered": (_I, [_P, _P, _L, _I, _P, _P, _P, _P, _L, _P]),
 }

@@ -77,6 +77,19 @@ __device__ __forceinline__ float warp_max(float v) {
 
 static inline int cdiv(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 
+// ---------------------------------------------------------------- per-device one-time state (a process may drive several GPUs)
+static inline int current_device() {
+    int d = 0;
+    cudaGetDevice(&d);
+    return d;
+}
+// true exactly once per (call site's mask, device): e.g. cudaFuncSetAttribute, which is a per-device setting
+static inline bool first_use_on_this_device(unsigned long long& mask) {
+    const unsigned long long bit = 1ull << (current_device() & 63);
+    const unsigned long long old = __atomic_fetch_or(&mask, bit, __ATOMIC_RELAXED);
+    return (old & bit) == 0;
+}
+
 // dispatch on the dtype tag
 #define SLLM_DISPATCH_DTYPE(dtype, ...)                                     \
     do {                                                                    \

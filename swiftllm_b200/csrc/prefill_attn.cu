@@ -19,10 +19,9 @@ static int launch_prefill(const void* q, const void* k, const void* v, void* o, 
                           const int32_t* seq_lens, float scale, int num_seqs, int max_len, int nq, int nkv,
                           int64_t qs, int64_t ks, int64_t vs, cudaStream_t stream) {
     const size_t smem = (size_t)PF_BQ * D * 2 + 2 * 2 * (size_t)PF_BK * D * 2;
-    static bool configured = false;
-    if (!configured) {
+    static unsigned long long configured = 0;
+    if (first_use_on_this_device(configured)) {
         cudaFuncSetAttribute(prefill_attn_kernel<T, D, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        configured = true;
     }
     dim3 grid(cdiv(max_len, PF_BQ), nq, num_seqs);
     prefill_attn_kernel<T, D, false><<<grid, PF_THREADS, smem, stream>>>((const T*)q, (const T*)k, (const T*)v, (T*)o, start_locs,

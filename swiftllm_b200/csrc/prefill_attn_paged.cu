@@ -19,10 +19,9 @@ static int launch_prefill_paged(const void* q, const void* k_cache, const void* 
                                 const int32_t* chunk_lens, float scale, int num_seqs, int max_chunk_len, int nq, int nkv,
                                 int64_t qs, const PfPagedKV& pk, cudaStream_t stream) {
     const size_t smem = (size_t)PF_BQ * D * 2 + 2 * 2 * (size_t)PF_BK * D * 2;
-    static bool configured = false;
-    if (!configured) {
+    static unsigned long long configured = 0;
+    if (first_use_on_this_device(configured)) {
         cudaFuncSetAttribute(prefill_attn_kernel<T, D, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        configured = true;
     }
     dim3 grid(cdiv(max_chunk_len, PF_BQ), nq, num_seqs);
     prefill_attn_kernel<T, D, true><<<grid, PF_THREADS, smem, stream>>>((const T*)q, (const T*)k_cache, (const T*)v_cache, (T*)o,
@@ -49,12 +48,12 @@ static int launch_prefill_paged_tc(const void* q, const void* k_cache, const voi
     p.o = o; p.start_locs = start_locs; p.seq_lens = chunk_lens; p.scale_log2e = scale_log2e; p.nq = nq; p.nkv = nkv;
     dim3 grid((max_chunk_len + 2 * PT_BQ - 1) / (2 * PT_BQ), nq, num_seqs);
     if (dtype == SLLM_F16) {
-        static bool c = false;
-        if (!c) { cudaFuncSetAttribute(prefill_attn_tc_kernel<__half, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, PT_SMEM_BYTES); c = true; }
+        static unsigned long long c = 0;
+        if (first_use_on_this_device(c)) cudaFuncSetAttribute(prefill_attn_tc_kernel<__half, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, PT_SMEM_BYTES);
         prefill_attn_tc_kernel<__half, true><<<grid, PT_THREADS, PT_SMEM_BYTES, stream>>>(qmap, kmap, vmap, p, pg);
     } else {
-        static bool c = false;
-        if (!c) { cudaFuncSetAttribute(prefill_attn_tc_kernel<__nv_bfloat16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, PT_SMEM_BYTES); c = true; }
+        static unsigned long long c = 0;
+        if (first_use_on_this_device(c)) cudaFuncSetAttribute(prefill_attn_tc_kernel<__nv_bfloat16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, PT_SMEM_BYTES);
         prefill_attn_tc_kernel<__nv_bfloat16, true><<<grid, PT_THREADS, PT_SMEM_BYTES, stream>>>(qmap, kmap, vmap, p, pg);
     }
     return check_launch("prefill_attention_paged(tcgen05)");

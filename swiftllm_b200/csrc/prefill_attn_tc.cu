@@ -59,12 +59,12 @@ int launch_prefill_tc(const void* q, const void* k, const void* v, void* o, cons
     p.o = o; p.start_locs = start_locs; p.seq_lens = seq_lens; p.scale_log2e = scale_log2e; p.nq = nq; p.nkv = nkv;
     dim3 grid((max_len + 2 * PT_BQ - 1) / (2 * PT_BQ), nq, num_seqs);
     if (dtype == SLLM_F16) {
-        static bool c = false;
-        if (!c) { cudaFuncSetAttribute(prefill_attn_tc_kernel<__half, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, PT_SMEM_BYTES); c = true; }
+        static unsigned long long c = 0;
+        if (first_use_on_this_device(c)) cudaFuncSetAttribute(prefill_attn_tc_kernel<__half, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, PT_SMEM_BYTES);
         prefill_attn_tc_kernel<__half, false><<<grid, PT_THREADS, PT_SMEM_BYTES, stream>>>(qmap, kmap, vmap, p, PtPaged{});
     } else {
-        static bool c = false;
-        if (!c) { cudaFuncSetAttribute(prefill_attn_tc_kernel<__nv_bfloat16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, PT_SMEM_BYTES); c = true; }
+        static unsigned long long c = 0;
+        if (first_use_on_this_device(c)) cudaFuncSetAttribute(prefill_attn_tc_kernel<__nv_bfloat16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, PT_SMEM_BYTES);
         prefill_attn_tc_kernel<__nv_bfloat16, false><<<grid, PT_THREADS, PT_SMEM_BYTES, stream>>>(qmap, kmap, vmap, p, PtPaged{});
     }
     return check_launch("prefill_attention(tcgen05)");

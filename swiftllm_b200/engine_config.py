@@ -31,7 +31,9 @@ class EngineConfig:
     # TP exchange: True = one-shot peer-memory all-reduce fused with add+RMSNorm (tp_comm.py), False = NCCL all-reduce +
     # a separate kernel, None = automatic (fused for tp_size 2..4 where it was measured faster, NCCL otherwise),
     # "two_shot" = the row-owner (reduce-scatter + all-gather) variant of the fused kernel, meant for tp_size 8,
-    # "two_shot_nvls" = the same with the reduction and the broadcast done by the NVSwitch (multimem.ld_reduce / multimem.st)
+    # "two_shot_nvls" = the same with the reduction and the broadcast done by the NVSwitch (multimem.ld_reduce / multimem.st),
+    # "ll" / "ll_nvls" = decode-sized exchanges (<= 1024 rows) through the barrier-free push kernel (csrc/allreduce_ll.cu: data
+    # lines carry their own epoch tag; "ll_nvls" broadcasts the normalised rows with one multimem.st), larger ones two-shot
     fused_allreduce: object = None
     # TP: shard lm_head by vocabulary rows (each rank computes logits of V/tp_size tokens; the greedy token is found with one
     # tiny all-gather of per-rank (max logit, argmax) pairs) instead of replicating the 1 GB matrix on every rank.

@@ -121,17 +121,18 @@ class LlamaModel:
 
         self.comm = None
         want_fused = getattr(self.engine_config, "fused_allreduce", None)
-        two_shot = want_fused in ("two_shot", "two_shot_nvls")      # opt-in (meant for TP 8) until measured on an 8-GPU box
-        nvls = want_fused == "two_shot_nvls"                         # in-switch reduction / broadcast (multimem)
+        two_shot = want_fused in ("two_shot", "two_shot_nvls", "ll", "ll_nvls")      # row-owner exchanges (meant for TP 8)
+        nvls = want_fused in ("two_shot_nvls", "ll_nvls")            # in-switch reduction / broadcast (multimem)
+        ll = want_fused in ("ll", "ll_nvls")                         # barrier-free push kernel for decode-sized exchanges
         if want_fused is None:
             want_fused = 2 <= self.tp_size <= 4          # measured: +7 % decode tokens/s at TP=2 and TP=4 on B200
         if self.tp_size > 1 and want_fused:
             from swiftllm_b200.worker.tp_comm import FusedAllReduce
             try:
                 self.comm = FusedAllReduce(self.engine_config.max_tokens_in_batch, self.model_config.hidden_size,
-                                           self.dtype, self.device, self.tp_group, two_shot=two_shot, nvls=nvls)
+                                           self.dtype, self.device, self.tp_group, two_shot=two_shot, nvls=nvls, ll=ll)
             except Exception as e:      # noqa: BLE001  (no peer access / symmetric memory unavailable)
-                if getattr(self.engine_config, "fused_allreduce", None) in (True, "two_shot", "two_shot_nvls"):
+                if getattr(self.engine_config, "fused_allreduce", None) in (True, "two_shot", "two_shot_nvls", "ll", "ll_nvls"):
                     raise
                 import warnings
                 warnings.warn(f"peer-memory exchange unavailable ({e}); using NCCL all-reduce")

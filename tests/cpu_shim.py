@@ -136,11 +136,12 @@ class GlooFusedAllReduce:
     normalised by it; its other residual rows are POISONED with NaN (the kernel simply does not maintain them), and the
     normalised rows are gathered from their owners."""
 
-    def __init__(self, max_tokens, hidden, dtype, device, group=None, two_shot=False, nvls=False):
+    def __init__(self, max_tokens, hidden, dtype, device, group=None, two_shot=False, nvls=False, ll=False):
         import torch.distributed as dist
         self.group = group if group is not None else dist.group.WORLD
         self.rank, self.world = dist.get_rank(self.group), dist.get_world_size(self.group)
-        self.two_shot, self.nvls, self.hidden, self.max_tokens = bool(two_shot) or bool(nvls), bool(nvls), hidden, max_tokens
+        self.two_shot, self.nvls, self.hidden, self.max_tokens = bool(two_shot) or bool(nvls) or bool(ll), bool(nvls), hidden, max_tokens
+        self.ll = bool(ll)        # the LL kernel has the two-shot kernel's observable semantics (row owners, sharded residual)
         self.data = torch.zeros((2, max_tokens, hidden), dtype=dtype)
 
     def partial_out(self, slot, num_tokens):

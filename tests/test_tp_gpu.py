@@ -21,8 +21,11 @@ MODES = [("nccl", False, False, False),
          ("fused-one-shot", True, False, False),
          ("fused-two-shot", "two_shot", False, False),
          ("fused-two-shot-nvls", "two_shot_nvls", False, False),
+         ("fused-ll", "ll", False, False),
+         ("fused-ll-nvls", "ll_nvls", False, False),
          ("nccl+sharded-lm-head+rotary-store", False, True, True),
-         ("two-shot+sharded-lm-head+rotary-store", "two_shot", True, True)]
+         ("two-shot+sharded-lm-head+rotary-store", "two_shot", True, True),
+         ("ll-nvls+sharded-lm-head+rotary-store", "ll_nvls", True, True)]
 
 
 def _run(rank, world, port, q, mode_names):
@@ -136,5 +139,18 @@ def test_tp_two_shot_exchange_and_sharded_lm_head_match_single_gpu(world):
         pytest.skip(f"needs {world} GPUs")
     names = ["fused-two-shot", "fused-two-shot-nvls", "nccl+sharded-lm-head+rotary-store", "two-shot+sharded-lm-head+rotary-store"]
     res = _spawn(world, names, 29690 + world)
+    print("TP parity (worst logit rel. err. vs TP=1):", world, res)
+    assert set(res) == set(names) and max(res.values()) <= 2 ** -5
+
+
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_tp_ll_push_exchange_matches_single_gpu(world):
+    """fused_allreduce="ll" / "ll_nvls": the barrier-free push exchange (csrc/allreduce_ll.cu; data lines carry their epoch tag)
+    for decode-sized steps - prompts of 40 + 7 + 129 = 176 rows (not divisible by the world size; some ranks own one row more)
+    and 3-row decode steps (fewer rows than ranks at world 4 / 8: ranks that own nothing), eager and in CUDA graphs."""
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs")
+    names = ["fused-ll", "fused-ll-nvls", "ll-nvls+sharded-lm-head+rotary-store"]
+    res = _spawn(world, names, 29730 + world)
     print("TP parity (worst logit rel. err. vs TP=1):", world, res)
     assert set(res) == set(names) and max(res.values()) <= 2 ** -5
