@@ -36,6 +36,12 @@ if DTYPE == "bf16":
 # travels with the repo snapshot): the UNMODIFIED kernels, compiled by the same Triton, only not recompiled.
 # REF_TRITON_CACHE_DIR overrides the location (the warm-up script points it at gpurun_out/).
 cache = os.environ.get("REF_TRITON_CACHE_DIR") or os.path.join(ROOT, "baseline", "_ref", "triton_cache", DTYPE)
+packed = os.path.join(ROOT, "baseline", "_ref", f"triton_cache_{DTYPE}.tar.gz")     # how the cache travels (it compresses 8x)
+if not os.environ.get("REF_TRITON_CACHE_DIR") and not os.path.isdir(cache) and os.path.exists(packed):
+    import tarfile
+    os.makedirs(os.path.dirname(cache), exist_ok=True)
+    with tarfile.open(packed) as tf:
+        tf.extractall(os.path.dirname(cache))
 os.makedirs(cache, exist_ok=True)
 os.environ["TRITON_CACHE_DIR"] = cache
 sys.path.insert(0, SRC)

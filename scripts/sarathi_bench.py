@@ -30,6 +30,9 @@ def main():
     ap.add_argument("--layers", type=int, default=0)
     ap.add_argument("--gpus", type=int, default=1, help="tensor-parallel degree (launch with torchrun --nproc-per-node N)")
     ap.add_argument("--model", type=str, default="llama3-8b", choices=["llama3-8b", "llama3-70b"])
+    ap.add_argument("--exchange", type=str, default="auto", choices=["auto", "nccl", "one_shot", "two_shot", "two_shot_nvls", "ll", "ll_nvls"],
+                    help="TP exchange (EngineConfig.fused_allreduce); auto = the library default for this TP degree")
+    ap.add_argument("--shard-lm-head", action="store_true")
     args = ap.parse_args()
     import torch.distributed as dist
     import swiftllm_b200
@@ -50,7 +53,9 @@ def main():
     bps = (max(S, args.prompt) + bs - 1) // bs + 2
     ec = swiftllm_b200.EngineConfig(model_path="", use_dummy=False, block_size=bs, gpu_mem_utilization=0.97, num_cpu_blocks=0,
                                     max_seqs_in_block_table=Bd + 1, max_blocks_per_seq=bps, max_batch_size=Bd + 1,
-                                    max_tokens_in_batch=args.chunk + Bd, dtype="bfloat16", tp_size=n, tp_rank=rank)
+                                    max_tokens_in_batch=args.chunk + Bd, dtype="bfloat16", tp_size=n, tp_rank=rank,
+                                    fused_allreduce={"auto": None, "nccl": False, "one_shot": True}.get(args.exchange, args.exchange),
+                                    shard_lm_head=args.shard_lm_head)
     with torch.inference_mode():
         m = swiftllm_b200.LlamaModel(ec, mc)
         m.load_weights(synthetic_getter(seed=0, std=0.02, device=dev))
@@ -102,7 +107,9 @@ def main():
                       f"{args.prompt}-token prompt + {Bd} decodes at seq_len {S} per step (BASELINE.json configs[2] / [4])", "layers": cfg["num_hidden_layers"]},
                       "piggybacked": {"ms_per_step": ms_pig, "tokens_per_s": tok / (ms_pig * 1e-3)},
                       "separate_calls": {"ms_per_step": ms_sep, "tokens_per_s": tok / (ms_sep * 1e-3)},
-                      "steps_timed": args.prompts * nchunks, "n_gpus": n, "parallelism": f"tp{n}", "data": "synthetic"}), flush=True)
+                      "steps_timed": args.prompts * nchunks, "n_gpus": n, "parallelism": f"tp{n}", "data": "synthetic",
+                      "exchange": args.exchange if m.comm is None or args.exchange != "auto" else ("ll" if getattr(m.comm, "ll", False) else "two_shot" if m.comm.two_shot else "one_shot"),
+                      "lm_head_sharded": bool(args.shard_lm_head)}), flush=True)
     if n > 1:
         torch.cuda.synchronize(); dist.barrier(); os._exit(0)
 

@@ -277,8 +277,7 @@ bool tc_paged_supported(int head_dim, int block_size, int nq, int nkv, int64_t n
 int launch_paged_tc(const void* q, const void* k_cache, const void* v_cache, const int32_t* block_table, const int32_t* seq_ids,
                     const int32_t* seq_lens, void* o, float* part_o, float* part_lse, float scale_log2e, int num_seqs,
                     int split_tokens, int num_splits, int cur_layer, int num_layers, int nq, int nkv, int max_blocks_per_seq,
-                    int64_t num_blocks, int64_t q_row_stride, sllm_dtype_t dtype, int num_sms, cudaStream_t stream,
-                    int* merged_in_kernel);
+                    int64_t num_blocks, int64_t q_row_stride, sllm_dtype_t dtype, int num_sms, cudaStream_t stream);
 
 // SLLM_PAGED_ATTN_GEN=1 forces the cp.async/mma.sync kernel (A/B measurements, debugging); default: tcgen05/TMA
 // whenever the shape is covered (head_dim 128, block_size 16).
@@ -291,9 +290,8 @@ template <typename T, int D>
 static int launch_paged(const PagedAttnParams& p, int num_seqs, int max_seq_len, cudaStream_t stream) {
     const size_t smem = (size_t)PA_STAGES * 2 * PA_TILE * D * 2 + (size_t)(p.split_tokens / p.block_size + 2) * sizeof(int32_t);
     static unsigned long long configured = 0;
-    if (first_use_on_this_device(configured)) {
+    if (first_use_on_this_device(configured))
         cudaFuncSetAttribute(paged_attn_kernel<T, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024);
-    }
     SLLM_REQUIRE(smem <= 110 * 1024, "paged_attention: split too long for shared memory (%zu bytes)", smem);
     dim3 grid(p.num_splits, p.nkv, num_seqs);
     paged_attn_kernel<T, D><<<grid, PA_THREADS, smem, stream>>>(p);
@@ -358,12 +356,11 @@ int sllm_paged_attention(const void* q, const void* k_cache, const void* v_cache
     cudaStream_t st = (cudaStream_t)stream;
     if (forced_generation() != 1 && tc_paged_supported(head_dim, block_size, nq, nkv, num_blocks, num_layers) &&
         dtype <= SLLM_BF16) {
-        int merged = 0;
         int e = launch_paged_tc(q, k_cache, v_cache, block_table, seq_ids, seq_lens, o, p.part_o, p.part_lse, p.scale_log2e,
                                 num_decoding_seqs, p.split_tokens, p.num_splits, cur_layer, num_layers, nq, nkv,
-                                max_blocks_per_seq, num_blocks, q_row_stride, dtype, num_sms(), st, &merged);
+                                max_blocks_per_seq, num_blocks, q_row_stride, dtype, num_sms(), st);
         if (e) return e;
-        if (p.num_splits > 1 && !merged) {
+        if (p.num_splits > 1) {
             dim3 g2(nq, num_decoding_seqs);
             SLLM_DISPATCH_DTYPE(dtype, (paged_attn_merge_kernel<T><<<g2, head_dim, 0, st>>>(p.part_o, p.part_lse, (T*)o, seq_lens, nq,
                                                                                           head_dim, p.num_splits, p.split_tokens)));

@@ -18,9 +18,6 @@
 // softmax uses all 128 threads; the GQA group is the N dimension (padded to 16 by reading neighbouring heads whose
 // columns are simply never read back).
 // HBM roofline: algorithmic bytes = sum_i len_i * nkv * 128 * 2 * sizeof(T) + 2 * Bd * nq * 128 * sizeof(T).
-#include <stdlib.h>
-
-#include <atomic>
 #include <mutex>
 #include <unordered_map>
 
@@ -50,9 +47,6 @@ struct TcParams {
     int split_tokens, num_splits, cur_layer, num_layers, nq, nkv, max_blocks_per_seq, num_seqs, num_items;
     // shared-memory placement of the 1 KiB atoms of a KV tile and the matching descriptor strides
     int page_stride, tg_stride, half_stride, k_sbo, v_lbo, v_sbo, tma_4d;
-    // flash-decoding splits merged in this kernel: one counter per (sequence, kv head), zero before the launch and zero again
-    // after it (the CTA that merges resets it); NULL = the caller launches paged_attn_merge_kernel
-    unsigned int* merge_counters;
 };
 
 struct Barriers {       // all mbarriers of the CTA (shared memory)
@@ -64,7 +58,7 @@ struct Barriers {       // all mbarriers of the CTA (shared memory)
     uint64_t o_full[2], o_empty[2];
 };
 
-struct Item { int seq, kvh, split, split_start, split_len, ntiles, len; };
+struct Item { int seq, kvh, split, split_start, split_len, ntiles; };
 
 __device__ __forceinline__ bool get_item(const TcParams& p, int idx, Item& it) {
     it.split = idx % p.num_splits;
@@ -74,7 +68,6 @@ __device__ __forceinline__ bool get_item(const TcParams& p, int idx, Item& it) {
     // provably warp-uniform for the compiler
     const int len = __shfl_sync(0xffffffffu, p.seq_lens[it.seq], 0);
     it.split_start = it.split * p.split_tokens;
-    it.len = len;
     if (it.split_start >= len) return false;
     it.split_len = min(p.split_tokens, len - it.split_start);
     it.ntiles = (it.split_len + TC_TILE - 1) / TC_TILE;
@@ -382,37 +375,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) paged_attn_tc_kernel(const __gr
                     }
                 }
             }
-            if (p.num_splits > 1 && p.merge_counters != nullptr) {
-                // ---- phase 2 (paged_attn.py:111-149) without a second launch: the CTA that writes the LAST partial of this
-                // (sequence, kv head) merges all of them ("last block" pattern: partials, device fence, counter; the reader
-                // fences again and reads through L2).
-                __threadfence();
-                named_bar_sync(1, 128);
-                unsigned int* ctr = p.merge_counters + (int64_t)it.seq * p.nkv + it.kvh;
-                if (row == 0) rp[64] = __uint_as_float(atomicAdd(ctr, 1u));
-                named_bar_sync(1, 128);
-                const unsigned int nvalid = (unsigned int)((it.len + p.split_tokens - 1) / p.split_tokens);
-                if (__float_as_uint(rp[64]) == nvalid - 1) {
-                    __threadfence();
-                    if (row == 0) *ctr = 0;                                 // ready for the next launch / graph replay
-#pragma unroll
-                    for (int h = 0; h < G; h++) {
-                        if (h < g) {
-                            const int head = it.kvh * g + h;
-                            const int64_t base = ((int64_t)it.seq * p.nq + head) * p.num_splits;
-                            float m = -INFINITY;
-                            for (unsigned int s2 = 0; s2 < nvalid; s2++) m = fmaxf(m, __ldcg(p.part_lse + base + s2));
-                            float Ls = 0.f, Os = 0.f;
-                            for (unsigned int s2 = 0; s2 < nvalid; s2++) {
-                                const float e2 = fast_exp2_tc(__ldcg(p.part_lse + base + s2) - m);
-                                Ls += e2;
-                                Os += e2 * __ldcg(p.part_o + (base + s2) * TC_D + row);
-                            }
-                            out[((int64_t)it.seq * p.nq + head) * TC_D + row] = Traits<T>::from_f(Os / Ls);
-                        }
-                    }
-                }
-            }
         }
     }
 
@@ -425,8 +387,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) paged_attn_tc_kernel(const __gr
 }  // namespace sllm
 
 namespace sllm {
-
-__device__ unsigned int g_tc_merge_counters[8 * 8192];
 
 // ------------------------------------------------------------------ host side
 namespace {
@@ -442,19 +402,8 @@ struct MapKeyHash {
 };
 std::mutex g_map_mutex;
 std::unordered_map<MapKey, CUtensorMap, MapKeyHash> g_maps;
-int g_kv_4d_ok = -1;            // -1 unknown, 0 the driver rejected the permuted-stride 4-D map, 1 usable (a driver property)
-
-// in-kernel merge of flash-decoding splits: counters per (sequence, kv head), zero-initialised with the module and reset by the
-// merging CTA.  Consecutive launches rotate through TC_MERGE_REGIONS regions so that two launches in flight on different streams
-// (or nodes of different CUDA graphs) never share counters.
-constexpr int TC_MERGE_REGIONS = 8;
-constexpr int TC_MERGE_REGION_SIZE = 8192;
-
-// SLLM_PAGED_ATTN_FUSED_MERGE=0 keeps the separate merge launch (A/B, debugging)
-bool fused_merge_enabled() {
-    const char* e = getenv("SLLM_PAGED_ATTN_FUSED_MERGE");
-    return !(e && e[0] == '0');
-}
+int g_kv_4d_ok = -1;            // -1 unknown, 0 the driver rejected the permuted-stride 4-D map, 1 usable (a property of the
+                                // driver's tensor-map encoder, identical for every device of the process)
 
 CUtensorMapDataType map_dtype(sllm_dtype_t dt) { return dt == SLLM_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16; }
 
@@ -516,8 +465,7 @@ bool tc_paged_supported(int head_dim, int block_size, int nq, int nkv, int64_t n
 int launch_paged_tc(const void* q, const void* k_cache, const void* v_cache, const int32_t* block_table, const int32_t* seq_ids,
                     const int32_t* seq_lens, void* o, float* part_o, float* part_lse, float scale_log2e, int num_seqs,
                     int split_tokens, int num_splits, int cur_layer, int num_layers, int nq, int nkv, int max_blocks_per_seq,
-                    int64_t num_blocks, int64_t q_row_stride, sllm_dtype_t dtype, int num_sms, cudaStream_t stream,
-                    int* merged_in_kernel) {
+                    int64_t num_blocks, int64_t q_row_stride, sllm_dtype_t dtype, int num_sms, cudaStream_t stream) {
     const uint64_t rows = (uint64_t)num_blocks * num_layers * nkv * TC_BS;
     CUtensorMap kmap, vmap, qmap;
     if (g_kv_4d_ok != 0) {
@@ -537,16 +485,6 @@ int launch_paged_tc(const void* q, const void* k_cache, const void* v_cache, con
     p.scale_log2e = scale_log2e; p.split_tokens = split_tokens; p.num_splits = num_splits; p.cur_layer = cur_layer;
     p.num_layers = num_layers; p.nq = nq; p.nkv = nkv; p.max_blocks_per_seq = max_blocks_per_seq; p.num_seqs = num_seqs;
     p.num_items = num_seqs * nkv * num_splits;
-    p.merge_counters = nullptr;
-    if (merged_in_kernel) *merged_in_kernel = 0;
-    if (num_splits > 1 && (int64_t)num_seqs * nkv <= TC_MERGE_REGION_SIZE && fused_merge_enabled()) {
-        static std::atomic<unsigned int> launch_seq{0};
-        void* base = nullptr;
-        if (cudaGetSymbolAddress(&base, g_tc_merge_counters) == cudaSuccess && base) {
-            p.merge_counters = reinterpret_cast<unsigned int*>(base) + (launch_seq.fetch_add(1) % TC_MERGE_REGIONS) * TC_MERGE_REGION_SIZE;
-            if (merged_in_kernel) *merged_in_kernel = 1;
-        }
-    }
     p.tma_4d = g_kv_4d_ok == 1;
     if (p.tma_4d) { p.page_stride = 4096; p.tg_stride = 2048; p.half_stride = 1024; p.k_sbo = 2048; p.v_lbo = 1024; p.v_sbo = 2048; }
     else          { p.page_stride = 2048; p.tg_stride = 1024; p.half_stride = 16384; p.k_sbo = 1024; p.v_lbo = 16384; p.v_sbo = 1024; }

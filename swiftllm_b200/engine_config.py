@@ -37,15 +37,21 @@ class EngineConfig:
     fused_allreduce: object = None
     # TP: shard lm_head by vocabulary rows (each rank computes logits of V/tp_size tokens; the greedy token is found with one
     # tiny all-gather of per-rank (max logit, argmax) pairs) instead of replicating the 1 GB matrix on every rank.
-    # SURVEY.md §8 f-3.  Opt-in until it has been measured on a multi-GPU box.
-    shard_lm_head: bool = False
+    # SURVEY.md §8 f-3.  None = automatic: sharded when tp_size >= 4 (at tp 2 the saved half-read of the matrix, ~135 us, is what
+    # the extra argmax-merge launches and the all-gather cost: measured equal, profiles/r2_tp_sweep_n2_b256.jsonl).
+    shard_lm_head: object = None
     # pure-decode steps: rotary embedding + KV store of the new rows in ONE launch per layer instead of two.
-    # Opt-in until it has run on a GPU.
-    fuse_rotary_store: bool = False
+    # Bit-identical to the two kernels (tests/test_decode_fusion_gpu.py); one launch less per layer.
+    fuse_rotary_store: bool = True
     # swap in / out with device-resident id lists and one gather/scatter kernel over the pinned, mapped swap space (no host
     # syncs) instead of `.tolist()` + cudaMemcpyAsync per run.  Needs pin_swap_space.  Opt-in until it has
     # run on a GPU.
     device_swap: bool = False
+    # swap copies run on a dedicated copy stream: swap_in_seqs / swap_out_seqs return as soon as the block
+    # tables are updated and the copy is enqueued; the next forward waits for it on the device right before its first KV-cache
+    # access.  (The wait cannot be later: freed blocks are handed out again lowest-id-first - the reference's order, which the
+    # block-index parity depends on - so the next step's KV store may target exactly the blocks being copied out.)
+    swap_on_copy_stream: bool = False
 
     @staticmethod
     def add_cli_args(parser: argparse.ArgumentParser):

@@ -31,7 +31,7 @@ class LlamaTransformerLayer:
         self.layer_id = layer_id
         self.tp_size = getattr(engine_config, "tp_size", 1)
         self.tp_group = tp_group
-        self.fuse_rotary_store = bool(getattr(engine_config, "fuse_rotary_store", False))
+        self.fuse_rotary_store = bool(getattr(engine_config, "fuse_rotary_store", True))
         self.comm = comm            # FusedAllReduce (tp_comm.py) or None -> NCCL all-reduce + separate add/norm kernels
         self.num_q_heads = model_config.num_q_heads // self.tp_size      # per-rank shard
         self.num_kv_heads = model_config.num_kv_heads // self.tp_size

@@ -104,6 +104,8 @@ class LlamaModel:
         # has completed (event per slot), so back-to-back forward_async calls never race the copy engine
         self._stage_ring = []
         self._stage_next = 0
+        self._swap_stream = None        # EngineConfig.swap_on_copy_stream: dedicated copy stream + "copies done" event
+        self._swap_done = None
 
     # ------------------------------------------------------------------ init
     @torch.inference_mode()
@@ -115,7 +117,7 @@ class LlamaModel:
         self.weight = load_weights(self.model_config, self.dtype, self.engine_config.model_path,
                                    self.engine_config.use_dummy, getter=weight_getter,
                                    tp_rank=self.tp_rank, tp_size=self.tp_size, device=self.device,
-                                   shard_lm_head=bool(getattr(self.engine_config, "shard_lm_head", False)))
+                                   shard_lm_head=self._shard_lm_head())
         cos, sin = build_rope_tables(self.model_config, self.dtype)
         self._cos_cached, self._sin_cached = cos.to(self.device), sin.to(self.device)
 
@@ -151,6 +153,12 @@ class LlamaModel:
         ]
         self.post_layer = LlamaPostLayer(self.model_config, self.weight, tp_group=self.tp_group, tp_rank=self.tp_rank,
                                          tp_size=self.tp_size)
+
+    def _shard_lm_head(self) -> bool:
+        want = getattr(self.engine_config, "shard_lm_head", None)
+        if want is None:
+            want = self.tp_size >= 4 and self.model_config.vocab_size % self.tp_size == 0
+        return bool(want) and self.tp_size > 1
 
     def _kvslot_bytes(self) -> int:
         return self.model_config.get_kvslot_size(self.dtype) // self.tp_size
@@ -220,6 +228,7 @@ class LlamaModel:
                  block_table=None) -> torch.Tensor:
         """model.py:228-249."""
         input_embds = self.pre_layer.forward(input_ids)
+        self._wait_for_swaps()          # first KV-cache access of the step is layer 0's store: pending swap copies must be done
         residual_buf = torch.zeros_like(input_embds)
         k_cache = self.k_cache if k_cache is None else k_cache
         v_cache = self.v_cache if v_cache is None else v_cache
@@ -253,6 +262,12 @@ class LlamaModel:
         else:
             slot[1].synchronize()                # no-op unless the copy engine is more than _STAGE_SLOTS steps behind
         return slot
+
+    def _wait_for_swaps(self):
+        """Device-side wait (no host sync) for swap copies enqueued on the copy stream since the last forward."""
+        if self._swap_done is not None and not (torch.cuda.is_available() and torch.cuda.is_current_stream_capturing()):
+            torch.cuda.current_stream().wait_event(self._swap_done)
+            self._swap_done = None
 
     def _stage_metadata(self, *parts):
         """One persistent pinned host buffer (ring of slots), one async H2D copy; returns int32 device views (one per list)."""
@@ -389,6 +404,7 @@ class LlamaModel:
         hv[:B] = flat_ids; hv[B:2 * B] = seq_ids_list; hv[2 * B:3 * B] = lens_list
         g["meta"].copy_(host, non_blocking=True)
         ev.record()
+        self._wait_for_swaps()
         g["graph"].replay()
         # the graph's static output is overwritten by the next replay: hand out a copy (stream-ordered, no sync)
         return g["tokens"].clone()
@@ -456,13 +472,29 @@ class LlamaModel:
         src_block_ids = src.gather_allocated_blocks_and_free(seq_ids, seq_ids_list=seq_ids_list)
         dst_block_ids = dst.allocate_blocks_for_seqs(seq_ids, seq_lengths, seq_ids_list=seq_ids_list,
                                                      target_lens_list=seq_lengths_list)
-        if getattr(self.engine_config, "device_swap", False):
-            # ids stay on the device, one gather/scatter kernel over the mapped swap space: the whole swap is sync-free
-            swiftllm_c.swap_blocks_device(src_block_ids.to(torch.int64), dst_block_ids, is_swap_in,
-                                          self.k_cache, self.v_cache, self.k_swap, self.v_swap)
+        device_ids = bool(getattr(self.engine_config, "device_swap", False))
+        if device_ids:
+            src_ids, dst_ids = src_block_ids.to(torch.int64), dst_block_ids
         else:
-            swiftllm_c.swap_blocks(src_block_ids.tolist(), dst_block_ids.tolist(), is_swap_in,
-                                   self.k_cache, self.v_cache, self.k_swap, self.v_swap)
+            src_ids, dst_ids = src_block_ids.tolist(), dst_block_ids.tolist()
+        copy = swiftllm_c.swap_blocks_device if device_ids else swiftllm_c.swap_blocks
+        if not getattr(self.engine_config, "swap_on_copy_stream", False):
+            # ids stay on the device (device_swap): one gather/scatter kernel over the mapped swap space, sync-free
+            copy(src_ids, dst_ids, is_swap_in, self.k_cache, self.v_cache, self.k_swap, self.v_swap)
+            return
+        # copy stream: the copy starts once everything enqueued so far on this stream (the block-table kernels above, the KV
+        # stores of earlier steps) has finished; the next forward waits for `_swap_done` before it touches the cache
+        if self._swap_stream is None:
+            self._swap_stream = torch.cuda.Stream(device=self.device)
+        ready = torch.cuda.Event()
+        ready.record()
+        with torch.cuda.stream(self._swap_stream):
+            self._swap_stream.wait_event(ready)
+            copy(src_ids, dst_ids, is_swap_in, self.k_cache, self.v_cache, self.k_swap, self.v_swap)
+            if device_ids and src_ids.is_cuda:       # the id tensors were allocated on the main stream
+                src_ids.record_stream(self._swap_stream); dst_ids.record_stream(self._swap_stream)
+            self._swap_done = torch.cuda.Event()
+            self._swap_done.record()
 
     @torch.inference_mode()
     def swap_in_seqs(self, seq_ids_list: list):

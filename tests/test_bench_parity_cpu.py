@@ -35,7 +35,10 @@ def test_parity_check_passes_and_detects_corruption():
         bench, m, ids, sids, lens = _setup()
         res = bench.parity_check(m, m.model_config, ids, sids, lens, n_rows=4, n_seqs=2)
         assert res["ok"] and len(res["attention_rows"]) == 4 * len({0, 1})        # 2-layer model: layers {0, 1}
-        assert all(s["token_equal"] or s["oracle_top1_margin"] <= 2 * s["logit_abs_err"] for s in res["sequences"])
+        assert all(s["token_equal"] or s["exact_top1_margin_rel"] <= 2 * s["product_logit_err_vs_exact"] for s in res["sequences"])
+        # on CPU the "product" runs the oracle's own kernels: it must sit exactly on the storage-dtype oracle
+        assert all(s["product_vs_storage_dtype_oracle"] <= 1e-3 for s in res["sequences"])
+        assert all(s["product_logit_err_vs_exact"] <= 2 * s["storage_dtype_oracle_logit_err_vs_exact"] + 1e-3 for s in res["sequences"])
         assert res["attention_worst_rel_err"] <= 2e-3
 
         # corrupt the attention output of the product: the check must fail

@@ -42,6 +42,28 @@ def _make_model(cfg, eng, weights, dtype="float16", graph=False):
     return m
 
 
+def _exact_arithmetic_oracle(cfg, eng, w):
+    """oracle.model.OracleLlama on the SAME 16-bit weights, with fp32 activations, fp64 attention and no intermediate rounding;
+    the rope tables are the model's (rounded to fp16 like the reference's, model.py:224-225)."""
+    import copy
+    from oracle import kernels as K
+    w32 = copy.copy(w)
+    w32.layers = []
+    for lw in w.layers:
+        l2 = OracleWeights.Layer()
+        for n in ("attn_norm", "ffn_norm", "q_proj", "k_proj", "v_proj", "o_proj", "up_gate_proj", "down_proj"):
+            setattr(l2, n, getattr(lw, n).float())
+        w32.layers.append(l2)
+    w32.wte, w32.lm_head, w32.final_norm = w.wte.float(), w.lm_head.float(), w.final_norm.float()
+    o = OracleLlama(cfg, w32, block_size=eng["block_size"], num_blocks=eng["num_blocks"], num_cpu_blocks=eng["num_cpu_blocks"],
+                    max_seqs_in_block_table=eng["max_seqs_in_block_table"], max_blocks_per_seq=eng["max_blocks_per_seq"],
+                    attn="exact", dtype=torch.float32)
+    rs = cfg.get("rope_scaling", 1.0)
+    cos, sin = K.rope_tables(o.D, cfg.get("rope_theta", 10000), cfg["max_position_embeddings"], 1.0 if rs is None else rs, torch.float16)
+    o.cos, o.sin = cos.float(), sin.float()
+    return o
+
+
 def _log(name, **kw):
     os.makedirs(OUT, exist_ok=True)
     with open(os.path.join(OUT, "parity_log.jsonl"), "a") as f:
@@ -53,15 +75,29 @@ def test_model_matches_reference_golden_trace(golden):
     cfg = json.loads(str(z["config"])); eng = json.loads(str(z["engine"]))
     w = OracleWeights.from_golden(z, cfg["num_hidden_layers"])
     m = _make_model(cfg, eng, w)
+    exact = _exact_arithmetic_oracle(cfg, eng, w)
     calls = json.loads(str(z["calls"]))
-    worst = 0.0
+    worst = worst_prod = worst_ref = 0.0
     for i, c in enumerate(calls):
+        getattr(exact, {"forward": "forward", "swap_out": "swap_out_seqs", "swap_in": "swap_in_seqs"}.get(c["op"], "free_seqs_resources"))(
+            *((c["input_ids"], c["seq_ids"], c["dec_lens"]) if c["op"] == "forward" else (c["seq_ids"],)))
         if c["op"] == "forward":
             toks = m.forward(c["input_ids"], c["seq_ids"], c["dec_lens"])
             ref = T(z[f"t{i}_logits"]).float()
             got = m.post_layer.last_logits.float().cpu()
             rel = float((got - ref).abs().max() / ref.abs().max())
             worst = max(worst, rel)
+            # the same network evaluated WITHOUT intermediate rounding (fp32 activations, fp64 attention, the fp16 weights and the
+            # fp16-rounded rope tables of the model): how far is the reference's own fp16 arithmetic from it, how far the product?
+            tru = exact.last_logits.double()
+            e_ref = float((ref.double() - tru).abs().max() / tru.abs().max())
+            e_prod = float((got.double() - tru).abs().max() / tru.abs().max())
+            worst_prod, worst_ref = max(worst_prod, e_prod), max(worst_ref, e_ref)
+            _log("golden_trace_vs_exact_arithmetic", step=i, reference_trace_err=e_ref, product_err=e_prod)
+            # north_star asks for logits "within 1e-3 relative": the reference's own trace is this far from exact arithmetic,
+            # (1.0-1.4e-3 on this trace), and the product - whose fp16 storage roundings are as many but not the same - must not be
+            # materially further: 1.5 x the reference's own error + one fp16 ulp of the largest logit
+            assert e_prod <= 1.5 * e_ref + 2 ** -11, (i, e_prod, e_ref)
             top2 = ref.topk(2, dim=1).values
             margin = float((top2[:, 0] - top2[:, 1]).min() / ref.abs().max())
             _log("golden_trace", step=i, rel_logit_err=rel, top1_margin_rel=margin, tokens_equal=toks == z[f"t{i}_tokens"].tolist())
@@ -86,7 +122,7 @@ def test_model_matches_reference_golden_trace(golden):
     kc, kref = m.k_cache.float().cpu(), T(z["k_cache_final"]).float()
     vc, vref = m.v_cache.float().cpu(), T(z["v_cache_final"]).float()
     assert (kc - kref).abs().max() <= 4e-3 * kref.abs().max() and (vc - vref).abs().max() <= 4e-3 * vref.abs().max()
-    _log("golden_trace_summary", worst_rel_logit_err=worst)
+    _log("golden_trace_summary", worst_rel_logit_err=worst, worst_product_err_vs_exact=worst_prod, worst_reference_err_vs_exact=worst_ref)
 
 
 TINY2 = dict(model_type="llama", num_hidden_layers=3, num_attention_heads=8, num_key_value_heads=2, hidden_size=1024,

@@ -50,5 +50,6 @@ def test_dry_run_decode_fusion_and_swap_gpu_tests():
     with product_on_cpu(_EXTRA):
         f.test_rotary_store_decode_equals_separate_kernels_and_oracle(torch.float16, dict(nq=4, nkv=2, D=64, bs=16))
         f.test_rotary_store_decode_equals_separate_kernels_and_oracle(torch.bfloat16, dict(nq=8, nkv=1, D=128, bs=32))
-        s.test_model_swap_with_device_ids_equals_memcpy_path()
+        for variant in (dict(device_swap=True), dict(swap_on_copy_stream=True), dict(device_swap=True, swap_on_copy_stream=True)):
+            s.test_model_swap_with_device_ids_equals_memcpy_path(variant)
     # (test_swap_blocks_device_ids_exact and the CUDA-graph model test need real pinned memory / graphs: GPU only)

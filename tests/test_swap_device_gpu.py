@@ -37,9 +37,14 @@ def test_swap_blocks_device_ids_exact(dtype):
         swiftllm_c.swap_blocks_device(i64(src), i64(dst), False, kcd, vcd, ks.clone(), vs.clone())
 
 
-def test_model_swap_with_device_ids_equals_memcpy_path():
-    """Preempt / resume through LlamaModel.swap_out_seqs / swap_in_seqs with device_swap=True: block tables, free maps, swap
-    space and cache contents equal the memcpy path's; decoding after the round trip gives the same tokens."""
+@pytest.mark.parametrize("variant", [dict(device_swap=True), dict(swap_on_copy_stream=True),
+                                     dict(device_swap=True, swap_on_copy_stream=True)],
+                         ids=["device-ids", "copy-stream", "device-ids+copy-stream"])
+def test_model_swap_with_device_ids_equals_memcpy_path(variant):
+    """Preempt / resume through LlamaModel.swap_out_seqs / swap_in_seqs with device_swap=True (ids stay on the device, one
+    gather kernel) and / or swap_on_copy_stream=True (the copy runs on a dedicated stream, the next forward waits for it on the
+    device): block tables, free maps, swap space and cache contents equal the memcpy path's; decoding between and after the swaps
+    gives the same tokens."""
     from test_chunked_prefill_gpu import CFG
     from test_model_gpu import _hf_tensors
     import swiftllm_b200
@@ -54,7 +59,7 @@ def test_model_swap_with_device_ids_equals_memcpy_path():
         m.load_weights(dict_getter(_hf_tensors(w, CFG["intermediate_size"])))
         m.init_kvcache_and_swap(96)
         return m
-    a, b = make(), make(device_swap=True)
+    a, b = make(), make(**variant)
     rng = np.random.default_rng(6)
     prompts = [rng.integers(0, 320, size=n).tolist() for n in (70, 5, 33)]
     sids = [2, 0, 5]

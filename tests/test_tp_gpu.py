@@ -118,7 +118,7 @@ def _spawn(world, mode_names, port):
     return results
 
 
-@pytest.mark.parametrize("world", [2, 4, 8])
+@pytest.mark.parametrize("world", [2, 4])
 def test_tp_matches_single_gpu(world):
     """NCCL all-reduce + add/norm kernel, and the one-shot fused peer-memory exchange, against TP = 1 (eager and CUDA graph)."""
     if torch.cuda.device_count() < world:
@@ -128,7 +128,7 @@ def test_tp_matches_single_gpu(world):
     assert set(res) == {"nccl", "fused-one-shot"} and max(res.values()) <= 2 ** -5
 
 
-@pytest.mark.parametrize("world", [2, 4, 8])
+@pytest.mark.parametrize("world", [2, 4])
 def test_tp_two_shot_exchange_and_sharded_lm_head_match_single_gpu(world):
     """fused_allreduce="two_shot" (row owner reduces + adds + normalises, pushes the row to every rank; residual sharded by
     rows) with peer loads / stores and with the NVSwitch doing the reduction and the broadcast (multimem.ld_reduce /
@@ -143,7 +143,7 @@ def test_tp_two_shot_exchange_and_sharded_lm_head_match_single_gpu(world):
     assert set(res) == set(names) and max(res.values()) <= 2 ** -5
 
 
-@pytest.mark.parametrize("world", [2, 4, 8])
+@pytest.mark.parametrize("world", [2, 4])
 def test_tp_ll_push_exchange_matches_single_gpu(world):
     """fused_allreduce="ll" / "ll_nvls": the barrier-free push exchange (csrc/allreduce_ll.cu; data lines carry their epoch tag)
     for decode-sized steps - prompts of 40 + 7 + 129 = 176 rows (not divisible by the world size; some ranks own one row more)
@@ -153,4 +153,15 @@ def test_tp_ll_push_exchange_matches_single_gpu(world):
     names = ["fused-ll", "fused-ll-nvls", "ll-nvls+sharded-lm-head+rotary-store"]
     res = _spawn(world, names, 29730 + world)
     print("TP parity (worst logit rel. err. vs TP=1):", world, res)
+    assert set(res) == set(names) and max(res.values()) <= 2 ** -5
+
+
+def test_tp_world8_every_mode_matches_single_gpu():
+    """World 8 (1 kv head / 2 q heads per rank; 3-row decode steps leave five ranks without a row to own): EVERY exchange / sharding
+    mode in ONE process group (an 8-GPU box is charged 8x: one torch import + NCCL init instead of one per mode)."""
+    if torch.cuda.device_count() < 8:
+        pytest.skip("needs 8 GPUs")
+    names = [m[0] for m in MODES]
+    res = _spawn(8, names, 29760)
+    print("TP parity (worst logit rel. err. vs TP=1):", 8, res)
     assert set(res) == set(names) and max(res.values()) <= 2 ** -5
