@@ -42,6 +42,15 @@ if not os.environ.get("REF_TRITON_CACHE_DIR") and not os.path.isdir(cache) and o
     os.makedirs(os.path.dirname(cache), exist_ok=True)
     with tarfile.open(packed) as tf:
         tf.extractall(os.path.dirname(cache))
+    # Triton's group files list their children by ABSOLUTE path (triton/runtime/cache.py: get_group drops children that do not
+    # exist, which turns every lookup into a miss after the cache has moved): point them at where the files are now
+    for d, _, fs in os.walk(cache):
+        for f in fs:
+            if f.startswith("__grp__") and f.endswith(".json"):
+                gp = os.path.join(d, f)
+                grp = json.load(open(gp))
+                grp["child_paths"] = {c: os.path.join(d, os.path.basename(pth)) for c, pth in grp.get("child_paths", {}).items()}
+                json.dump(grp, open(gp, "w"))
 os.makedirs(cache, exist_ok=True)
 os.environ["TRITON_CACHE_DIR"] = cache
 sys.path.insert(0, SRC)
