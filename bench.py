@@ -79,7 +79,8 @@ def parse():
                     help="skip timing the unmodified reference's Triton path (baseline/_ref/src) on this GPU (N = 1 only)")
     ap.add_argument("--ref-triton-dtypes", type=str, default="fp16,bf16",
                     help="reference Triton arm: fp16 = the tree as shipped, bf16 = its fp16 literals patched in a temp copy")
-    ap.add_argument("--ref-triton-timeout", type=int, default=240, help="seconds per dtype for the reference Triton arm")
+    ap.add_argument("--ref-triton-timeout", type=int, default=150,
+                    help="seconds per dtype for the reference Triton arm (a cache hit takes ~25 s; a cold JIT needs ~8 min and is cut off)")
     ap.add_argument("--no-parity", action="store_true", help="skip the oracle parity check at the benchmarked shape")
     ap.add_argument("--parity-seqs", type=int, default=2, help="sequences re-run through the CPU oracle (tokens + logits)")
     ap.add_argument("--no-live-traffic", action="store_true", help="skip the ncu DRAM-byte measurement of the decode kernel")

@@ -11,7 +11,8 @@ from ctypes import c_char_p, c_float, c_int, c_int64, c_void_p
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libswiftllm_b200.so")
+# SLLM_LIB_PATH: a development variant of the library (python -m swiftllm_b200.build with SLLM_BUILD_VARIANT); never set by tests / bench
+LIB_PATH = os.environ.get("SLLM_LIB_PATH") or os.path.join(_HERE, "libswiftllm_b200.so")
 
 F16, BF16 = 0, 1
 

@@ -13,11 +13,14 @@ from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-OBJ = os.path.join(CSRC, "build")
-LIB = os.path.join(HERE, "libswiftllm_b200.so")
+# development variants (e.g. SLLM_BUILD_VARIANT=trace SLLM_NVCC_EXTRA=-DSLLM_PT_TRACE): separate objects and library name; the
+# product library is always the plain one
+_VARIANT = os.environ.get("SLLM_BUILD_VARIANT", "")
+OBJ = os.path.join(CSRC, "build" + ("_" + _VARIANT if _VARIANT else ""))
+LIB = os.path.join(HERE, "libswiftllm_b200" + ("_" + _VARIANT if _VARIANT else "") + ".so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",
-         "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-Xptxas", "-v"]
+         "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-Xptxas", "-v"] + os.environ.get("SLLM_NVCC_EXTRA", "").split()
 
 
 def sources():

@@ -29,7 +29,8 @@ class EngineConfig:
     use_cuda_graph: bool = False    # capture pure-decode steps into CUDA graphs
     max_cuda_graphs: int = 16       # decode graphs kept (keyed by batch size x length bucket), least recently used evicted
     # TP exchange: True = one-shot peer-memory all-reduce fused with add+RMSNorm (tp_comm.py), False = NCCL all-reduce +
-    # a separate kernel, None = automatic (fused for tp_size 2..4 where it was measured faster, NCCL otherwise),
+    # a separate kernel, None = automatic (what was measured fastest: one-shot at tp_size 2 and 4, "two_shot_nvls" at 8 with
+    # "two_shot" and then NCCL as fall-backs when multicast / peer memory is unavailable),
     # "two_shot" = the row-owner (reduce-scatter + all-gather) variant of the fused kernel, meant for tp_size 8,
     # "two_shot_nvls" = the same with the reduction and the broadcast done by the NVSwitch (multimem.ld_reduce / multimem.st),
     # "ll" / "ll_nvls" = decode-sized exchanges (<= 1024 rows) through the barrier-free push kernel (csrc/allreduce_ll.cu: data
@@ -37,8 +38,8 @@ class EngineConfig:
     fused_allreduce: object = None
     # TP: shard lm_head by vocabulary rows (each rank computes logits of V/tp_size tokens; the greedy token is found with one
     # tiny all-gather of per-rank (max logit, argmax) pairs) instead of replicating the 1 GB matrix on every rank.
-    # SURVEY.md §8 f-3.  None = automatic: sharded when tp_size >= 4 (at tp 2 the saved half-read of the matrix, ~135 us, is what
-    # the extra argmax-merge launches and the all-gather cost: measured equal, profiles/r2_tp_sweep_n2_b256.jsonl).
+    # SURVEY.md §8 f-3.  None = automatic: sharded whenever tp_size > 1 and divides the vocabulary (measured on B200, decode
+    # batch 256: -0.10 / -0.15 / -0.20 ms per step at tp 2 / 4 / 8, profiles/r2_tp_sweep_*.jsonl).
     shard_lm_head: object = None
     # pure-decode steps: rotary embedding + KV store of the new rows in ONE launch per layer instead of two.
     # Bit-identical to the two kernels (tests/test_decode_fusion_gpu.py); one launch less per layer.

@@ -51,7 +51,8 @@ class LlamaTransformerLayer:
         infer_state: LlamaInferState,
     ) -> torch.Tensor:
         mc, w = self.model_config, self.weight
-        comm = self.comm
+        # fused exchange (tp_comm.py) for steps it covers; the same choice in every layer of a step (the row count is fixed)
+        comm = self.comm if (self.comm is not None and residual_buf.shape[0] <= self.comm.max_fused_tokens) else None
         if comm is not None and self.layer_id > 0:
             # the previous layer left its down_proj PARTIAL in symmetric buffer 1: exchange + add + norm in one kernel
             input_embds = comm.reduce_add_norm(1, residual_buf.shape[0], residual_buf, w.attn_norm, mc.rms_norm_eps)

@@ -123,27 +123,35 @@ class LlamaModel:
 
         self.comm = None
         want_fused = getattr(self.engine_config, "fused_allreduce", None)
-        two_shot = want_fused in ("two_shot", "two_shot_nvls", "ll", "ll_nvls")      # row-owner exchanges (meant for TP 8)
-        nvls = want_fused in ("two_shot_nvls", "ll_nvls")            # in-switch reduction / broadcast (multimem)
-        ll = want_fused in ("ll", "ll_nvls")                         # barrier-free push kernel for decode-sized exchanges
+        explicit = want_fused is not None
         if want_fused is None:
-            want_fused = 2 <= self.tp_size <= 4          # measured: +7 % decode tokens/s at TP=2 and TP=4 on B200
-        if self.tp_size > 1 and want_fused:
+            # measured on B200 / NVSwitch (profiles/r2_tp_sweep_*.jsonl), decode batch 256 x 4096:
+            #   tp 2, 4: one-shot peer-memory kernel (14 / 21 us per exchange vs NCCL 22 / 30 us + the add/norm launch)
+            #   tp 8:    row-owner kernel with in-switch reduction and broadcast (24.6 us vs NCCL 33.7 + 3.2 us)
+            candidates = [True] if 2 <= self.tp_size <= 4 else (["two_shot_nvls", "two_shot"] if self.tp_size == 8 else [])
+        else:
+            candidates = [want_fused] if want_fused else []
+        for cand in candidates if self.tp_size > 1 else []:
+            two_shot = cand in ("two_shot", "two_shot_nvls", "ll", "ll_nvls")      # row-owner exchanges
+            nvls = cand in ("two_shot_nvls", "ll_nvls")                            # in-switch reduction / broadcast (multimem)
+            ll = cand in ("ll", "ll_nvls")                                         # barrier-free push kernel
             from swiftllm_b200.worker.tp_comm import FusedAllReduce
+            comm = None
             try:
-                self.comm = FusedAllReduce(self.engine_config.max_tokens_in_batch, self.model_config.hidden_size,
-                                           self.dtype, self.device, self.tp_group, two_shot=two_shot, nvls=nvls, ll=ll)
-            except Exception as e:      # noqa: BLE001  (no peer access / symmetric memory unavailable)
-                if getattr(self.engine_config, "fused_allreduce", None) in (True, "two_shot", "two_shot_nvls", "ll", "ll_nvls"):
+                comm = FusedAllReduce(self.engine_config.max_tokens_in_batch, self.model_config.hidden_size,
+                                      self.dtype, self.device, self.tp_group, two_shot=two_shot, nvls=nvls, ll=ll)
+            except Exception as e:      # noqa: BLE001  (no peer access / symmetric memory / multicast unavailable)
+                if explicit:
                     raise
                 import warnings
-                warnings.warn(f"peer-memory exchange unavailable ({e}); using NCCL all-reduce")
-                self.comm = None
+                warnings.warn(f"fused exchange `{cand}` unavailable ({e}); trying the next option")
             # every rank must take the same path
-            ok = torch.tensor([1 if self.comm is not None else 0], device=self.device)
+            ok = torch.tensor([1 if comm is not None else 0], device=self.device)
             dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=self.tp_group)
-            if int(ok.item()) == 0:
-                self.comm = None
+            if int(ok.item()) == 1:
+                self.comm = comm
+                break
+            del comm
         decoding_piggyback_stream = torch.cuda.Stream()
         self.pre_layer = LlamaPreLayer(self.model_config, self.weight)
         self.transformer_layers = [
@@ -157,7 +165,7 @@ class LlamaModel:
     def _shard_lm_head(self) -> bool:
         want = getattr(self.engine_config, "shard_lm_head", None)
         if want is None:
-            want = self.tp_size >= 4 and self.model_config.vocab_size % self.tp_size == 0
+            want = self.tp_size >= 2 and self.model_config.vocab_size % self.tp_size == 0
         return bool(want) and self.tp_size > 1
 
     def _kvslot_bytes(self) -> int:
@@ -236,7 +244,7 @@ class LlamaModel:
             block_table = self.gpu_block_manager.block_table
         for layer in self.transformer_layers:
             input_embds = layer.forward(input_embds, residual_buf, k_cache, v_cache, block_table, infer_state)
-        if self.comm is not None:
+        if self.comm is not None and residual_buf.shape[0] <= self.comm.max_fused_tokens:
             # the last layer's down_proj partials are still un-reduced: exchange + add + final RMSNorm in one kernel
             normed = self.comm.reduce_add_norm(1, residual_buf.shape[0], residual_buf, self.weight.final_norm,
                                                self.model_config.rms_norm_eps)

@@ -18,6 +18,10 @@ from swiftllm_b200 import _lib
 
 NUM_SLOTS = 2
 MAX_LL_TOKENS = 1024        # exchanges of at most this many token rows take the barrier-free LL kernel (ll=True)
+# Row-owner (two-shot / NVLS / LL) exchanges are used for steps of at most this many token rows - the range they were run and
+# measured in on 8 GPUs (decode batches of 256 and 1024, 576-row mixed steps); larger steps (whole-prompt prefill) take the NCCL
+# all-reduce + add/norm path, where the exchange is bandwidth-bound and a fused kernel has nothing to add.
+MAX_ROW_OWNER_TOKENS = 1024
 
 
 class FusedAllReduce:
@@ -33,12 +37,15 @@ class FusedAllReduce:
         group = group if group is not None else dist.group.WORLD
         self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
         assert 2 <= self.world <= 8
-        self.max_tokens, self.hidden, self.dtype, self.device = max_tokens, hidden, dtype, device
+        self.hidden, self.dtype, self.device = hidden, dtype, device
         self.ll = bool(ll)              # decode-sized exchanges: barrier-free push kernel (csrc/allreduce_ll.cu); row ownership,
         #                                 residual sharding and the returned buffer are those of the two-shot kernel, which
         #                                 also serves the exchanges that are too large for the LL receive buffers
         self.two_shot = bool(two_shot) or bool(nvls) or self.ll
         self.nvls = bool(nvls)          # two-shot with in-switch reduction / broadcast (multimem.ld_reduce / multimem.st)
+        # steps with more token rows than this do not go through this object (the layers fall back to NCCL + add/norm)
+        self.max_fused_tokens = min(max_tokens, MAX_ROW_OWNER_TOKENS) if self.two_shot else max_tokens
+        self.max_tokens = max_tokens = self.max_fused_tokens
         self.data = symm_mem.empty((NUM_SLOTS, max_tokens, hidden), dtype=dtype, device=device)
         self.flags = symm_mem.empty((16 * 8,), dtype=torch.int32, device=device)
         self.data.zero_(); self.flags.zero_()

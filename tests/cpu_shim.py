@@ -141,6 +141,7 @@ class GlooFusedAllReduce:
         self.group = group if group is not None else dist.group.WORLD
         self.rank, self.world = dist.get_rank(self.group), dist.get_world_size(self.group)
         self.two_shot, self.nvls, self.hidden, self.max_tokens = bool(two_shot) or bool(nvls) or bool(ll), bool(nvls), hidden, max_tokens
+        self.max_fused_tokens = max_tokens
         self.ll = bool(ll)        # the LL kernel has the two-shot kernel's observable semantics (row owners, sharded residual)
         self.data = torch.zeros((2, max_tokens, hidden), dtype=dtype)
 
