@@ -1,6 +1,5 @@
 #!/bin/bash
-# 1-GPU: final validation of the shipped build + the prefill scheduling experiment (variant libraries) + the reference arm with the
-# relocated Triton cache.
+# 1-GPU: final validation of the shipped build + the reference arm with the relocated Triton cache.
 #   gpurun --timeout 600 -- 'bash scripts/gpu_r2_final.sh'
 set -u
 mkdir -p gpurun_out
@@ -17,19 +16,9 @@ except Exception as e: print('   no line', e)"
 done
 echo "== prefill kernel, shipped library"
 timeout 200 python scripts/prefill_bench.py > gpurun_out/prefill_bench_shipped.jsonl 2>/dev/null; echo "rc=$?"
-echo "== GPU suite + prefill kernel + one-CTA timeline, ping-pong variant"
-SLLM_LIB_PATH=$PWD/swiftllm_b200/libswiftllm_b200_pp.so timeout 300 python -m pytest tests -m gpu -q -p no:cacheprovider --maxfail=5 --deselect tests/test_cabi.py > gpurun_out/pytest_pp.log 2>&1; echo "rc=$?"; tail -3 gpurun_out/pytest_pp.log | cut -c1-300
-SLLM_LIB_PATH=$PWD/swiftllm_b200/libswiftllm_b200_pp.so timeout 200 python scripts/prefill_bench.py > gpurun_out/prefill_bench_pp.jsonl 2>/dev/null; echo "rc=$?"
-python - <<'PY'
-import json
-for tag in ("shipped","pp"):
-    try:
-        for l in open(f'gpurun_out/prefill_bench_{tag}.jsonl'):
-            d=json.loads(l)
-            if 'tflops' in d and not d['gen'].startswith('gen1'): print('  ', tag.ljust(8), d['gen'][:30].ljust(30), d.get('Bp'), d.get('L'), round(d['ms'],3), 'ms', round(d['tflops']), 'TF/s', 'x FA2', round(d.get('speedup_over_reference_flash_attn',0),2))
-    except Exception as e: print('   ', tag, 'no data', e)
-PY
-timeout 120 python scripts/prefill_trace.py > gpurun_out/prefill_trace_pp.txt 2>&1; echo "trace rc=$?"; head -30 gpurun_out/prefill_trace_pp.txt | cut -c1-160
+# (the run of this script in round 2 also executed the suite, the prefill bench and a one-CTA timeline with the "ping-pong" scheduling
+#  variant of the prefill kernel - commit 5f0c0d1^..; it was 4 % slower and was removed: profiles/r2_prefill_pingpong_trace.txt,
+#  profiles/r2_prefill_bench_pingpong_variant.jsonl)
 echo "== bench.py (N=1, quick: no reference arm / CPU baseline / prefill; parity on 1 sequence)"
 timeout 300 python bench.py --steps 20 --warmup 3 --no-ref-triton --no-cpu-baseline --no-prefill --parity-seqs 1 > gpurun_out/bench_n1_quick.json 2> gpurun_out/bench_n1_quick.err; echo "rc=$?"
 python - <<'PY'

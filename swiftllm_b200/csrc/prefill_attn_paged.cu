@@ -10,13 +10,7 @@
 #include <stdlib.h>
 
 #include "prefill_attn_kernel.cuh"
-// -DSLLM_PT_PINGPONG (development variant, scripts/gpu_prefill_pingpong.sh): the scheduling experiment of round 2 - S issued per
-// tile, exp2 phases of the two softmax groups in strict alternation - lives in its own header until it has been validated
-#ifdef SLLM_PT_PINGPONG
-#include "prefill_attn_tc_kernel_pp.cuh"
-#else
 #include "prefill_attn_tc_kernel.cuh"
-#endif
 
 namespace sllm {
 

@@ -4,13 +4,7 @@
 #include <mutex>
 #include <unordered_map>
 
-// -DSLLM_PT_PINGPONG (development variant, scripts/gpu_prefill_pingpong.sh): the scheduling experiment of round 2 - S issued per
-// tile, exp2 phases of the two softmax groups in strict alternation - lives in its own header until it has been validated
-#ifdef SLLM_PT_PINGPONG
-#include "prefill_attn_tc_kernel_pp.cuh"
-#else
 #include "prefill_attn_tc_kernel.cuh"
-#endif
 
 namespace sllm {
 
@@ -77,10 +71,3 @@ int launch_prefill_tc(const void* q, const void* k, const void* v, void* o, cons
 }
 
 }  // namespace sllm
-
-#ifdef SLLM_PT_TRACE
-// development builds only (scripts/prefill_trace.py): the timeline recorded by the traced CTA
-extern "C" int sllm_debug_prefill_trace(void* host_out, long long bytes) {
-    return (int)cudaMemcpyFromSymbol(host_out, sllm::g_pt_trace, (size_t)bytes);
-}
-#endif
