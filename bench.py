@@ -596,6 +596,10 @@ def run_ours(args):
         tj = json.load(open(tpath))
         traffic, traffic_src = tj["dram_bytes_read"] + tj["dram_bytes_write"], f"committed constant, {tj['source']} (live ncu: {traffic_src})"
 
+    # rank 0 may have spent ~10 s in the ncu subprocess: meet at a HOST-level barrier (NCCL, no watchdog) before the next
+    # collective step, so that no rank sits inside a fused exchange kernel (which traps after ~1-2 minutes of spinning) meanwhile
+    barrier()
+
     # ---- parity at the benchmarked shape (outside the timed regions): sampled attention rows + whole sequences vs the oracle
     parity = None
     if not args.no_parity and args.model != "llama3-70b":
