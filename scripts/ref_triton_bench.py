@@ -32,7 +32,7 @@ if DTYPE == "bf16":
     assert npatched >= 10, npatched
 # Triton JIT cache.  The reference's phase-1 kernel unrolls seq_block_size / block_size = 128 pages (tl.static_range,
 # paged_attn.py:88) and is specialised three times on cur_layer: ~8 minutes of ptxas on a cold cache.  A cache built once on a
-# B200 box of this image (scripts/gpu_r2_warm_triton_cache.sh) is kept under baseline/_ref/triton_cache/<dtype> (git-ignored,
+# B200 box of this image (scripts/gpu_r2_session_e.sh) is kept under baseline/_ref/triton_cache/<dtype> (git-ignored,
 # travels with the repo snapshot): the UNMODIFIED kernels, compiled by the same Triton, only not recompiled.
 # REF_TRITON_CACHE_DIR overrides the location (the warm-up script points it at gpurun_out/).
 cache = os.environ.get("REF_TRITON_CACHE_DIR") or os.path.join(ROOT, "baseline", "_ref", "triton_cache", DTYPE)

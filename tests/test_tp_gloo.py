@@ -91,9 +91,16 @@ def _worker_model(rank, world, port, ret, shard_lm_head=False, comm=None):
         ec = swiftllm_b200.EngineConfig(model_path="", use_dummy=False, block_size=16, gpu_mem_utilization=0.9, num_cpu_blocks=2,
                                         max_seqs_in_block_table=8, max_blocks_per_seq=8, max_batch_size=8, max_tokens_in_batch=128,
                                         dtype="float16", tp_size=world, tp_rank=rank, shard_lm_head=shard_lm_head,
-                                        fused_allreduce={None: False, "one_shot": True, "two_shot": "two_shot", "ll": "ll", "two_shot+limit": "two_shot"}[comm])
+                                        fused_allreduce={None: False, "one_shot": True, "two_shot": "two_shot", "ll": "ll", "two_shot+limit": "two_shot",
+                                                         "auto": None}[comm])
         m = swiftllm_b200.LlamaModel(ec, swiftllm_b200.LlamaModelConfig(cfg))
         m.load_weights(dict_getter(_hf_tensors(w, cfg["intermediate_size"])))
+        if comm == "auto":                                 # the library's own choice for this TP degree (EngineConfig defaults)
+            ec.shard_lm_head = None
+            m = swiftllm_b200.LlamaModel(ec, swiftllm_b200.LlamaModelConfig(cfg))
+            m.load_weights(dict_getter(_hf_tensors(w, cfg["intermediate_size"])))
+            assert m.comm is not None and not m.comm.two_shot and m.weight.lm_head_sharded     # tp 2..4: one-shot, sharded lm_head
+            shard_lm_head = True
         assert m.weight.lm_head.shape[0] == (cfg["vocab_size"] // world if shard_lm_head else cfg["vocab_size"])
         m.init_kvcache_and_swap(20)
         m.post_layer.keep_logits = True
@@ -161,7 +168,7 @@ def test_sharded_argmax_merge_prefers_the_first_occurrence():
         assert merge_sharded_argmax(pairs).tolist() == [first(logits[b]) for b in range(B)]
 
 
-@pytest.mark.parametrize("comm", ["one_shot", "two_shot", "ll", "two_shot+limit"])
+@pytest.mark.parametrize("comm", ["one_shot", "two_shot", "ll", "two_shot+limit", "auto"])
 @pytest.mark.parametrize("world", [2, 3])
 def test_product_model_fused_exchange_host_path_on_cpu(world, comm):
     """The host side of the fused exchange (GEMM partials written into the comm buffer, layer i's down_proj exchange folded
@@ -169,10 +176,11 @@ def test_product_model_fused_exchange_host_path_on_cpu(world, comm):
     a rank owns) with a gloo stand-in that follows the CUDA kernels' semantics (tests/cpu_shim.py: GlooFusedAllReduce; rows a
     rank does not own are poisoned with NaN there).  world 3 leaves T = 2 tokens without an owner on one rank.
     "two_shot+limit": steps with more rows than the exchange object covers (max_fused_tokens; whole-prompt prefill in production)
-    take the all-reduce + add/norm path while the 2-row decode steps of the same model take the fused path."""
+    take the all-reduce + add/norm path while the 2-row decode steps of the same model take the fused path.
+    "auto": `fused_allreduce=None`, `shard_lm_head=None` - the candidate loop of `LlamaModel.load_weights` and the defaults it picks."""
     ctx = mp.get_context("spawn")
     ret = ctx.Queue()
-    port = 29700 + world + {"one_shot": 0, "two_shot": 10, "ll": 20, "two_shot+limit": 30}[comm]
+    port = 29700 + world + {"one_shot": 0, "two_shot": 10, "ll": 20, "two_shot+limit": 30, "auto": 40}[comm]
     procs = [ctx.Process(target=_worker_model_w, args=(r, world, port, ret, comm)) for r in range(world)]
     for p in procs:
         p.start()
