@@ -358,99 +358,109 @@ def parity_check(model, mc, ids, sids, lens, n_rows=8, n_seqs=2, tp_rank=0, tp_s
         dist.barrier()                                           # rank 0 is running the CPU oracle
         return None
 
-    res = {"attention_rows": [], "sequences": [], "tp": tp_size}
-    worst = 0.0
-    for li in layers:
-        q, o = cap[li]
-        for (b, h) in picks:
-            nb = (lens[b] + bs - 1) // bs
-            blocks = bt[sids[b], :nb].long()
-            kk = model.k_cache[blocks, li, h].cpu().unsqueeze(1).unsqueeze(1)       # [nb, 1, 1, bs, D]
-            vv = model.v_cache[blocks, li, h].cpu().unsqueeze(1).unsqueeze(1)
-            qq = q[b, h * g:(h + 1) * g].cpu().unsqueeze(0)                          # [1, g, D]
-            ref = K.paged_attention_exact(qq, kk, vv, torch.arange(nb, dtype=torch.int32).unsqueeze(0), [0], [lens[b]],
-                                          D ** -0.5, bs, 0)                          # fp64 [1, g*D]
-            got = o[b, h * g * D:(h + 1) * g * D].double().cpu()
-            err = float((got - ref[0]).abs().max() / ref.abs().max())
-            worst = max(worst, err)
-            res["attention_rows"].append({"layer": li, "seq": b, "kv_head": h + tp_rank * nkv, "rel_err_vs_fp64": err})
-    res["attention_worst_rel_err"] = worst
-    res["attention_tol"] = 8e-3
-    assert worst <= 8e-3, f"paged attention at the benchmarked shape is off the fp64 oracle by {worst:.3e} (> 8e-3 of max|o|)"
-
-    # (b) whole sequences through the CPU oracle with the unsharded weights and this cache's pages
-    if n_seqs > 0:
-        NQ, NKV, Fd = mc.num_q_heads, mc.num_kv_heads, mc.ffn_inter_dim
-        w = OracleWeights(L)
-        if tp_size == 1:
-            mw = model.weight
-            w.wte, w.lm_head, w.final_norm = mw.wte.cpu(), mw.lm_head.cpu(), mw.final_norm.cpu()
-            nqd, nkvd = NQ * D, NKV * D
-            for lw, ml in zip(w.layers, mw.layers):
-                qkv = ml.qkv_proj.cpu()
-                lw.q_proj, lw.k_proj, lw.v_proj = qkv[:nqd], qkv[nqd:nqd + nkvd], qkv[nqd + nkvd:]
-                lw.attn_norm, lw.ffn_norm = ml.attn_norm.cpu(), ml.ffn_norm.cpu()
-                lw.o_proj, lw.up_gate_proj, lw.down_proj = ml.o_proj.cpu(), ml.up_gate_proj.cpu(), ml.down_proj.cpu()
-        else:
-            # the shards came from a deterministic getter: regenerate the FULL tensors (same bits every rank sliced from)
-            H, V, dt = mc.hidden_size, mc.vocab_size, model.dtype
-            get = lambda key, shape: full_getter(key, shape, dt).to(dt).cpu()
-            w.wte, w.lm_head, w.final_norm = get("model.embed_tokens.weight", (V, H)), get("lm_head.weight", (V, H)), get("model.norm.weight", (H,))
-            for i, lw in enumerate(w.layers):
-                pre = f"model.layers.{i}."
-                lw.attn_norm, lw.ffn_norm = get(pre + "input_layernorm.weight", (H,)), get(pre + "post_attention_layernorm.weight", (H,))
-                lw.q_proj = get(pre + "self_attn.q_proj.weight", (H, H))
-                lw.k_proj, lw.v_proj = get(pre + "self_attn.k_proj.weight", (NKV * D, H)), get(pre + "self_attn.v_proj.weight", (NKV * D, H))
-                lw.o_proj = get(pre + "self_attn.o_proj.weight", (H, H))
-                lw.up_gate_proj = torch.cat((get(pre + "mlp.up_proj.weight", (Fd, H)), get(pre + "mlp.gate_proj.weight", (Fd, H))), dim=0)
-                lw.down_proj = get(pre + "mlp.down_proj.weight", (H, Fd))
-        bps = max((lens[b] + bs - 1) // bs for b in seqs)
-        cfgd = dict(hidden_size=mc.hidden_size, num_attention_heads=NQ, num_key_value_heads=NKV, intermediate_size=Fd,
-                    num_hidden_layers=L, vocab_size=mc.vocab_size, rms_norm_eps=mc.rms_norm_eps, rope_theta=mc.rope_theta,
-                    max_position_embeddings=mc.max_position_embeddings, rope_scaling=mc.rope_scaling)
-        def run_oracle(weights, dtype, tables=None):
-            orc = OracleLlama(cfgd, weights, block_size=bs, num_blocks=len(seqs) * bps, num_cpu_blocks=0, max_seqs_in_block_table=len(seqs),
-                              max_blocks_per_seq=bps, attn="exact", dtype=dtype)
-            if tables is not None:
-                orc.cos, orc.sin = tables                                        # the model's tables (rounded to the storage dtype)
-            for j, b in enumerate(seqs):
+    def _parity_rank0(res):
+        worst = 0.0
+        for li in layers:
+            q, o = cap[li]
+            for (b, h) in picks:
                 nb = (lens[b] + bs - 1) // bs
-                orc.k_cache[j * bps:j * bps + nb] = kv[b][0].to(dtype)
-                orc.v_cache[j * bps:j * bps + nb] = kv[b][1].to(dtype)
-                orc.gpu_block_manager.allocate_blocks_for_seqs([j], [lens[b]])   # lowest ids first -> j*bps .. j*bps+nb-1
-                assert list(np.asarray(orc.gpu_block_manager.block_table[j][:nb])) == list(range(j * bps, j * bps + nb))
-            t = orc.forward([ids[b] for b in seqs], list(range(len(seqs))), [lens[b] for b in seqs])
-            return t, orc.last_logits.double(), (orc.cos, orc.sin)
+                blocks = bt[sids[b], :nb].long()
+                kk = model.k_cache[blocks, li, h].cpu().unsqueeze(1).unsqueeze(1)       # [nb, 1, 1, bs, D]
+                vv = model.v_cache[blocks, li, h].cpu().unsqueeze(1).unsqueeze(1)
+                qq = q[b, h * g:(h + 1) * g].cpu().unsqueeze(0)                          # [1, g, D]
+                ref = K.paged_attention_exact(qq, kk, vv, torch.arange(nb, dtype=torch.int32).unsqueeze(0), [0], [lens[b]],
+                                              D ** -0.5, bs, 0)                          # fp64 [1, g*D]
+                got = o[b, h * g * D:(h + 1) * g * D].double().cpu()
+                err = float((got - ref[0]).abs().max() / ref.abs().max())
+                worst = max(worst, err)
+                res["attention_rows"].append({"layer": li, "seq": b, "kv_head": h + tp_rank * nkv, "rel_err_vs_fp64": err})
+        res["attention_worst_rel_err"] = worst
+        res["attention_tol"] = 8e-3
+        assert worst <= 8e-3, f"paged attention at the benchmarked shape is off the fp64 oracle by {worst:.3e} (> 8e-3 of max|o|)"
 
-        # (i) the oracle in the storage dtype (the reference's rounding points restated, CPU GEMMs), (ii) the SAME inputs (16-bit
-        # weights, 16-bit cache pages, the model's rounded rope tables) evaluated in fp32 without any intermediate rounding (fp64
-        # attention): the definition both (i) and the product approximate.  The product must be as close to (ii) as (i) is:
-        # over 32 layers, 16-bit storage rounding alone puts two correct implementations ~3-4 % of max|logit| apart.
-        ref_toks, ref_logits, tables = run_oracle(w, model.dtype)
-        for lw in w.layers:
-            for n_ in ("attn_norm", "ffn_norm", "q_proj", "k_proj", "v_proj", "o_proj", "up_gate_proj", "down_proj"):
-                setattr(lw, n_, getattr(lw, n_).float())
-        w.wte, w.lm_head, w.final_norm = w.wte.float(), w.lm_head.float(), w.final_norm.float()
-        true_toks, true_logits, _ = run_oracle(w, torch.float32, (tables[0].float(), tables[1].float()))
-        for j, b in enumerate(seqs):
-            tl_, rl, gl = true_logits[j], ref_logits[j], logits[b].double()
-            scale = float(tl_.abs().max())
-            err_prod, err_orc = float((gl - tl_).abs().max()) / scale, float((rl - tl_).abs().max()) / scale
-            top2 = torch.topk(tl_, 2).values
-            margin = float(top2[0] - top2[1])
-            same = int(toks[b]) == int(true_toks[j])
-            res["sequences"].append({"seq": b, "token": int(toks[b]), "exact_arithmetic_token": int(true_toks[j]), "storage_dtype_oracle_token": int(ref_toks[j]),
-                                     "token_equal": same, "product_logit_err_vs_exact": err_prod, "storage_dtype_oracle_logit_err_vs_exact": err_orc,
-                                     "product_vs_storage_dtype_oracle": float((gl - rl).abs().max()) / scale,
-                                     "exact_top1_margin_rel": margin / scale})
-            assert err_prod <= max(2.0 * err_orc, 2 ** -6), \
-                f"sequence {b}: product logits are {err_prod:.3e} of max|logit| from exact arithmetic, the storage-dtype oracle only {err_orc:.3e}"
-            assert same or margin <= 2 * err_prod * scale, \
-                f"sequence {b}: token {toks[b]} != exact-arithmetic token {true_toks[j]} with top-1 margin {margin / scale:.3e} > 2 x logit error {err_prod:.3e}"
-        res["logit_criterion"] = "product error vs exact arithmetic <= max(2 x the storage-dtype oracle's own error, 2^-6)"
-    res["ok"] = True
-    if tp_size > 1:
-        dist.barrier()
+        # (b) whole sequences through the CPU oracle with the unsharded weights and this cache's pages
+        if n_seqs > 0:
+            NQ, NKV, Fd = mc.num_q_heads, mc.num_kv_heads, mc.ffn_inter_dim
+            w = OracleWeights(L)
+            if tp_size == 1:
+                mw = model.weight
+                w.wte, w.lm_head, w.final_norm = mw.wte.cpu(), mw.lm_head.cpu(), mw.final_norm.cpu()
+                nqd, nkvd = NQ * D, NKV * D
+                for lw, ml in zip(w.layers, mw.layers):
+                    qkv = ml.qkv_proj.cpu()
+                    lw.q_proj, lw.k_proj, lw.v_proj = qkv[:nqd], qkv[nqd:nqd + nkvd], qkv[nqd + nkvd:]
+                    lw.attn_norm, lw.ffn_norm = ml.attn_norm.cpu(), ml.ffn_norm.cpu()
+                    lw.o_proj, lw.up_gate_proj, lw.down_proj = ml.o_proj.cpu(), ml.up_gate_proj.cpu(), ml.down_proj.cpu()
+            else:
+                # the shards came from a deterministic getter: regenerate the FULL tensors (same bits every rank sliced from)
+                H, V, dt = mc.hidden_size, mc.vocab_size, model.dtype
+                get = lambda key, shape: full_getter(key, shape, dt).to(dt).cpu()
+                w.wte, w.lm_head, w.final_norm = get("model.embed_tokens.weight", (V, H)), get("lm_head.weight", (V, H)), get("model.norm.weight", (H,))
+                for i, lw in enumerate(w.layers):
+                    pre = f"model.layers.{i}."
+                    lw.attn_norm, lw.ffn_norm = get(pre + "input_layernorm.weight", (H,)), get(pre + "post_attention_layernorm.weight", (H,))
+                    lw.q_proj = get(pre + "self_attn.q_proj.weight", (H, H))
+                    lw.k_proj, lw.v_proj = get(pre + "self_attn.k_proj.weight", (NKV * D, H)), get(pre + "self_attn.v_proj.weight", (NKV * D, H))
+                    lw.o_proj = get(pre + "self_attn.o_proj.weight", (H, H))
+                    lw.up_gate_proj = torch.cat((get(pre + "mlp.up_proj.weight", (Fd, H)), get(pre + "mlp.gate_proj.weight", (Fd, H))), dim=0)
+                    lw.down_proj = get(pre + "mlp.down_proj.weight", (H, Fd))
+            bps = max((lens[b] + bs - 1) // bs for b in seqs)
+            cfgd = dict(hidden_size=mc.hidden_size, num_attention_heads=NQ, num_key_value_heads=NKV, intermediate_size=Fd,
+                        num_hidden_layers=L, vocab_size=mc.vocab_size, rms_norm_eps=mc.rms_norm_eps, rope_theta=mc.rope_theta,
+                        max_position_embeddings=mc.max_position_embeddings, rope_scaling=mc.rope_scaling)
+            def run_oracle(weights, dtype, tables=None):
+                orc = OracleLlama(cfgd, weights, block_size=bs, num_blocks=len(seqs) * bps, num_cpu_blocks=0, max_seqs_in_block_table=len(seqs),
+                                  max_blocks_per_seq=bps, attn="exact", dtype=dtype)
+                if tables is not None:
+                    orc.cos, orc.sin = tables                                        # the model's tables (rounded to the storage dtype)
+                for j, b in enumerate(seqs):
+                    nb = (lens[b] + bs - 1) // bs
+                    orc.k_cache[j * bps:j * bps + nb] = kv[b][0].to(dtype)
+                    orc.v_cache[j * bps:j * bps + nb] = kv[b][1].to(dtype)
+                    orc.gpu_block_manager.allocate_blocks_for_seqs([j], [lens[b]])   # lowest ids first -> j*bps .. j*bps+nb-1
+                    assert list(np.asarray(orc.gpu_block_manager.block_table[j][:nb])) == list(range(j * bps, j * bps + nb))
+                t = orc.forward([ids[b] for b in seqs], list(range(len(seqs))), [lens[b] for b in seqs])
+                return t, orc.last_logits.double(), (orc.cos, orc.sin)
+
+            # (i) the oracle in the storage dtype (the reference's rounding points restated, CPU GEMMs), (ii) the SAME inputs (16-bit
+            # weights, 16-bit cache pages, the model's rounded rope tables) evaluated in fp32 without any intermediate rounding (fp64
+            # attention): the definition both (i) and the product approximate.  The product must be as close to (ii) as (i) is:
+            # over 32 layers, 16-bit storage rounding alone puts two correct implementations ~3-4 % of max|logit| apart.
+            ref_toks, ref_logits, tables = run_oracle(w, model.dtype)
+            for lw in w.layers:
+                for n_ in ("attn_norm", "ffn_norm", "q_proj", "k_proj", "v_proj", "o_proj", "up_gate_proj", "down_proj"):
+                    setattr(lw, n_, getattr(lw, n_).float())
+            w.wte, w.lm_head, w.final_norm = w.wte.float(), w.lm_head.float(), w.final_norm.float()
+            true_toks, true_logits, _ = run_oracle(w, torch.float32, (tables[0].float(), tables[1].float()))
+            for j, b in enumerate(seqs):
+                tl_, rl, gl = true_logits[j], ref_logits[j], logits[b].double()
+                scale = float(tl_.abs().max())
+                err_prod, err_orc = float((gl - tl_).abs().max()) / scale, float((rl - tl_).abs().max()) / scale
+                top2 = torch.topk(tl_, 2).values
+                margin = float(top2[0] - top2[1])
+                same = int(toks[b]) == int(true_toks[j])
+                res["sequences"].append({"seq": b, "token": int(toks[b]), "exact_arithmetic_token": int(true_toks[j]), "storage_dtype_oracle_token": int(ref_toks[j]),
+                                         "token_equal": same, "product_logit_err_vs_exact": err_prod, "storage_dtype_oracle_logit_err_vs_exact": err_orc,
+                                         "product_vs_storage_dtype_oracle": float((gl - rl).abs().max()) / scale,
+                                         "exact_top1_margin_rel": margin / scale})
+                assert err_prod <= max(2.0 * err_orc, 2 ** -6), \
+                    f"sequence {b}: product logits are {err_prod:.3e} of max|logit| from exact arithmetic, the storage-dtype oracle only {err_orc:.3e}"
+                assert same or margin <= 2 * err_prod * scale, \
+                    f"sequence {b}: token {toks[b]} != exact-arithmetic token {true_toks[j]} with top-1 margin {margin / scale:.3e} > 2 x logit error {err_prod:.3e}"
+            res["logit_criterion"] = "product error vs exact arithmetic <= max(2 x the storage-dtype oracle's own error, 2^-6)"
+
+    res = {"attention_rows": [], "sequences": [], "tp": tp_size}
+    try:
+        _parity_rank0(res)
+        res["ok"] = True
+    except AssertionError as e:
+        # TP: the other ranks wait at the barrier below and the line must still be printed (marked invalid); TP = 1: fail the run
+        res["ok"], res["error"] = False, str(e)[:400]
+        if tp_size == 1:
+            raise
+    finally:
+        if tp_size > 1:
+            dist.barrier()
     return res
 
 
@@ -683,6 +693,8 @@ def run_ours(args):
         line["reference_triton"] = blk
     if args.layers:
         line["reduced"] = "layer count overridden: NOT a valid BASELINE measurement"
+    if parity is not None and not parity.get("ok", False):
+        line["invalid"] = "the oracle parity check at the benchmarked shape FAILED: " + str(parity.get("error"))
     stage("done")
     emit(line)
     _finish_distributed(model, n)
