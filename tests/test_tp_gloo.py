@@ -191,11 +191,34 @@ def test_product_model_fused_exchange_host_path_on_cpu(world, comm):
     assert all(oks), oks
 
 
-def _worker_model_w(rank, world, port, ret, comm):
+@pytest.mark.slow_cpu
+@pytest.mark.parametrize("comm", ["two_shot", "one_shot", None], ids=["row-owner", "one-shot", "all-reduce"])
+def test_product_model_world8_host_path_on_cpu(comm):
+    """World 8 (the TP degree of BASELINE configs[3] / [4]): the host path with the row-owner exchange family that is the default
+    there (two-shot semantics: 2-row decode steps leave six ranks without a row to own) and the vocabulary-sharded lm_head, over
+    gloo with oracle-backed kernels.  8 processes on the CPU container."""
+    world = 8
+    ctx = mp.get_context("spawn")
+    ret = ctx.Queue()
+    port = 29790 + {"two_shot": 0, "one_shot": 1, None: 2}[comm]
+    procs = [ctx.Process(target=_worker_model_w, args=(r, world, port, ret, comm, True)) for r in range(world)]
+    for p in procs:
+        p.start()
+    oks = ret.get(timeout=600)
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    assert all(oks), oks
+
+
+def _worker_model_w(rank, world, port, ret, comm, shard_lm_head=False):
     global CFG
     if world == 3:                                         # heads / FFN columns must divide by the world size
         CFG = dict(CFG, num_attention_heads=6, num_key_value_heads=3, hidden_size=96, intermediate_size=192)
-    _worker_model(rank, world, port, ret, False, comm)
+    if world == 8:                                         # 1 kv head / 2 q heads per rank, like Llama-3 at TP 8 per kv head
+        CFG = dict(CFG, num_attention_heads=16, num_key_value_heads=8, hidden_size=256, intermediate_size=256)
+    torch.set_num_threads(1 if world > 4 else torch.get_num_threads())
+    _worker_model(rank, world, port, ret, shard_lm_head, comm)
 
 
 def _worker_chunked(rank, world, port, ret):
