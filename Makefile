@@ -1,7 +1,7 @@
 # Convenience targets (everything is plain python underneath).
 PY ?= python
 
-.PHONY: build test test-gpu test-pending bench smoke sass-check reference clean
+.PHONY: build test test-gpu bench smoke sass-check reference clean
 
 build:            ## nvcc -gencode arch=compute_100a,code=sm_100a -> swiftllm_b200/libswiftllm_b200.so
 	$(PY) -m swiftllm_b200.build
@@ -9,11 +9,8 @@ build:            ## nvcc -gencode arch=compute_100a,code=sm_100a -> swiftllm_b2
 test: build       ## CPU suite: oracle vs golden vectors, host logic, C-ABI surface, gloo TP, dry runs, mirrors
 	$(PY) -m pytest tests -q -m "not gpu"
 
-test-gpu: build   ## parity through the C ABI on a B200 (validated tests; pending ones are skipped)
+test-gpu: build   ## parity through the C ABI on a B200 (multi-GPU cases skip themselves when the box has fewer devices)
 	$(PY) -m pytest tests -q -m gpu
-
-test-pending: build   ## first GPU run of the tests marked pending_gpu
-	SLLM_RUN_PENDING=1 $(PY) -m pytest tests -q -m gpu -k "chunked or decode_fusion or swap_device or two_shot or sharded"
 
 bench: build      ## one JSON line: decode tokens/s of BASELINE.json configs[1] on one B200
 	$(PY) bench.py
@@ -24,7 +21,7 @@ smoke: build
 sass-check: build ## validated kernels still compile to their validated instruction streams
 	$(PY) -m pytest tests/test_cabi.py -q -k validated
 
-reference:        ## the unmodified reference under baseline/_ref (for scripts/ref_triton_bench.py)
+reference:        ## the unmodified reference under baseline/_ref (for scripts/ref_triton_bench.py / the reference_triton block of bench.py)
 	bash scripts/install_reference.sh
 
 clean:

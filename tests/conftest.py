@@ -13,8 +13,8 @@ GOLDEN_DIR = os.path.join(ROOT, "tests", "golden")
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run with -m gpu on the B200 box)")
     config.addinivalue_line("markers", "slow_cpu: CPU test that takes tens of seconds")
-    config.addinivalue_line("markers", "pending_gpu: GPU test of code that was written and cross-compiled when no GPU time was "
-                                       "left (never executed on hardware yet); skipped unless SLLM_RUN_PENDING=1")
+    config.addinivalue_line("markers", "pending_gpu: GPU test of code that has not run on hardware yet; skipped unless "
+                                       "SLLM_RUN_PENDING=1 (no test carries it at the moment: everything has run on a B200)")
 
 
 def pytest_collection_modifyitems(config, items):
