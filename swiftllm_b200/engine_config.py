@@ -45,8 +45,8 @@ class EngineConfig:
     # Bit-identical to the two kernels (tests/test_decode_fusion_gpu.py); one launch less per layer.
     fuse_rotary_store: bool = True
     # swap in / out with device-resident id lists and one gather/scatter kernel over the pinned, mapped swap space (no host
-    # syncs) instead of `.tolist()` + cudaMemcpyAsync per run.  Needs pin_swap_space.  Validated on B200 (tests/test_swap_device_gpu.py);
-    # opt-in because it changes nothing a caller can observe except the absence of the two host syncs.
+    # syncs) instead of `.tolist()` + cudaMemcpyAsync per run.  Needs pin_swap_space.  Validated on B200
+    # (tests/test_swap_device_gpu.py); opt-in: its copy speed (SM loads / stores over PCIe) against the DMA path is unmeasured.
     device_swap: bool = False
     # swap copies run on a dedicated copy stream: swap_in_seqs / swap_out_seqs return as soon as the block
     # tables are updated and the copy is enqueued; the next forward waits for it on the device right before its first KV-cache
