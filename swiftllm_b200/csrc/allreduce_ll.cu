@@ -221,11 +221,14 @@ extern "C" int sllm_allreduce_add_rmsnorm_ll(const void* partial, void* const* h
     if (threads < 32) threads = 32;
     const size_t smem = (size_t)nvec * sizeof(uint4);
     SLLM_REQUIRE(smem <= 48 * 1024, "allreduce(LL): hidden %d too large", hidden);
-    int dev = 0, sms = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    if (sms <= 0) sms = 148;
-    const int64_t cap = 2LL * sms;                                   // every CTA must be resident: 2 x 512 threads per SM always fit
+    static int sm_count[64] = {0};                                   // per device (a process may drive several)
+    const int dev = current_device() & 63;
+    if (sm_count[dev] == 0) {
+        int n = 0;
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        sm_count[dev] = n > 0 ? n : 148;
+    }
+    const int64_t cap = 2LL * sm_count[dev];                         // every CTA must be resident: 2 x 512 threads per SM always fit
     const unsigned grid = (unsigned)(num_tokens < cap ? num_tokens : cap);
     cudaStream_t st = (cudaStream_t)stream;
     const bool nvls = mc_ag_recv != nullptr;
